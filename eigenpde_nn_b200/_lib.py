@@ -1,0 +1,83 @@
+"""ctypes binding of libeigenpde_b200.so (include/eigenpde_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  The library is never built implicitly on import.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeigenpde_b200.so")
+
+EPDE_MAX_LAYERS = 8
+EPDE_MAX_K = 8
+ACT_IDS = {"Tanh": 0, "Sigmoid": 1, "Softplus": 2, "LogSigmoid": 3, "ELU": 4, "CELU": 4, "ReLU": 5,
+           "Tanhshrink": 6}
+FLAG_SORT = 1
+
+EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
+           "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
+           "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step"]
+
+
+class EpdeDesc(C.Structure):
+    _fields_ = [("d", C.c_int32), ("d_pad", C.c_int32), ("k", C.c_int32), ("n_layers", C.c_int32),
+                ("widths", C.c_int32 * (EPDE_MAX_LAYERS + 1)), ("act_id", C.c_int32), ("flags", C.c_uint32)]
+
+
+class EpdeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EpdeError("%s not found: build it with `python -m eigenpde_nn_b200.build` "
+                            "(there is no CPU or PyTorch fallback for the step)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i64, f64, sz = C.c_void_p, C.c_int64, C.c_double, C.c_size_t
+        dp = C.POINTER(EpdeDesc)
+        L.epde_abi_version.restype = C.c_int
+        L.epde_error_string.restype = C.c_char_p
+        L.epde_error_string.argtypes = [C.c_int]
+        L.epde_param_count.argtypes = [dp, C.POINTER(i64)]
+        L.epde_num_sums.argtypes = [dp, C.POINTER(C.c_int32)]
+        L.epde_has_fused_path.argtypes = [dp]
+        L.epde_workspace_bytes.argtypes = [dp, i64, C.POINTER(sz)]
+        L.epde_step_partial.argtypes = [dp, vp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
+        L.epde_step_finish.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, vp, sz, vp, vp, vp]
+        L.epde_step.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp, vp]
+        L.epde_forward.argtypes = [dp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
+        L.epde_minibatch_indices.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, vp]
+        L.epde_mt_seed.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_int32)]
+        L.epde_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, i64, vp]
+        for name in EXPORTS:
+            if name != "epde_error_string":
+                getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise EpdeError("%s failed: %d (%s)" % (what, rc, lib().epde_error_string(rc).decode()))
+
+
+def make_desc(arch, k, activation_name, d_pad, sort=True) -> EpdeDesc:
+    """arch = [d, n_1, ..., n_{L-1}, 1] (src/pytorch_eigen_solver.py:352)."""
+    if len(arch) - 1 > EPDE_MAX_LAYERS:
+        raise EpdeError("too many layers")
+    D = EpdeDesc()
+    D.d, D.d_pad, D.k, D.n_layers = int(arch[0]), int(d_pad), int(k), len(arch) - 1
+    for i, n in enumerate(arch):
+        D.widths[i] = int(n)
+    # unknown activation names fall back to CELU in the reference (src/network_arch.py:27-32)
+    D.act_id = ACT_IDS.get(activation_name, ACT_IDS["CELU"])
+    D.flags = FLAG_SORT if sort else 0
+    return D

@@ -1,0 +1,390 @@
+// C ABI of libeigenpde_b200.so (see include/eigenpde_b200.h) and the small glue kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/eigenpde_b200.h"
+#include "epde_fused.cuh"
+#include "epde_generic.cuh"
+
+using namespace epde;
+
+namespace {
+
+constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
+constexpr int kFusedH = 20;
+constexpr size_t kSumsTail = 2048;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_desc(const epde_desc* D) {
+  if (!D) return EPDE_ERR_NULL;
+  if (D->k < 1 || D->k > EPDE_MAX_K) return EPDE_ERR_DESC;
+  if (D->n_layers < 1 || D->n_layers > EPDE_MAX_LAYERS) return EPDE_ERR_DESC;
+  if (D->d < 1 || D->widths[0] != D->d) return EPDE_ERR_DESC;
+  if (D->d_pad < D->d || (D->d_pad & 3)) return EPDE_ERR_ALIGN;
+  for (int l = 1; l <= D->n_layers; l++)
+    if (D->widths[l] < 1 || D->widths[l] > 4096) return EPDE_ERR_DESC;
+  if (D->widths[D->n_layers] != 1) return EPDE_ERR_DESC;
+  if (D->act_id < EPDE_ACT_TANH || D->act_id > EPDE_ACT_TANHSHRINK) return EPDE_ERR_DESC;
+  return EPDE_OK;
+}
+
+bool fused_ok(const epde_desc* D) {
+  if (D->n_layers != 4 || D->act_id != EPDE_ACT_TANH) return false;
+  if (D->widths[1] != kFusedH || D->widths[2] != kFusedH || D->widths[3] != kFusedH) return false;
+  if (D->k > 6) return false;
+  return pass2_smem_bytes<kFusedH>(D->d, D->d_pad) <= 227 * 1024 &&
+         (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + 4096 <= 200 * 1024;
+}
+
+int64_t param_count(const epde_desc* D) {
+  int64_t n = 0;
+  for (int l = 1; l <= D->n_layers; l++) n += (int64_t)D->widths[l] * D->widths[l - 1] + D->widths[l];
+  return n * D->k;
+}
+
+int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
+
+// ---- workspace ------------------------------------------------------------------------------
+struct FusedWs {
+  float* pw; float* ybuf; double* part; Coef* coef; float* pg; size_t total;
+};
+FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
+  char* p = (char*)base; size_t off = 0; FusedWs W;
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off = align_up(off + bytes, 256); return r; };
+  W.pw = (float*)take((size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4);
+  W.ybuf = (float*)take((size_t)B * D->k * 4);
+  W.part = (double*)take((size_t)kMaxCtas * num_sums(D->k) * 8);
+  W.coef = (Coef*)take(sizeof(Coef));
+  W.pg = (float*)take((size_t)kMaxCtas * GradLayout<kFusedH>(D->d_pad).total() * 4);
+  W.total = off;
+  return W;
+}
+
+int sm_count(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (*out > kMaxCtas) *out = kMaxCtas;
+  return 0;
+}
+
+// sum the per-CTA partials in CTA order -> sums[NS]
+__global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restrict__ sums) {
+  const int s = threadIdx.x;
+  if (s >= ns) return;
+  double v = 0.0;
+  for (int b = 0; b < nb; b++) v += part[(size_t)b * ns + s];
+  sums[s] = v;
+}
+
+struct EigW { double v[EPDE_MAX_K]; };
+
+// Everything that depends only on the batch-global sums: eig_vals, cvec, losses
+// (src/pytorch_eigen_solver.py:215-229, 177-189) and the per-sample seed coefficients of the
+// reverse pass (SURVEY.md 8(a) closed form).  One thread; k <= 8.
+__global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
+                       double* __restrict__ out, Coef* __restrict__ coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double W = sums[0];
+  const double* S1 = sums + 1;
+  const double* E = sums + 1 + k;
+  const double* S2 = sums + 1 + 2 * k;
+  double m[EPDE_MAX_K], var[EPDE_MAX_K], Rq[EPDE_MAX_K], lam[EPDE_MAX_K], wt[EPDE_MAX_K];
+  double cov[EPDE_MAX_K][EPDE_MAX_K];
+  int cvec[EPDE_MAX_K];
+  for (int i = 0; i < k; i++) m[i] = S1[i] / W;
+  int t = 0;
+  for (int i = 0; i < k; i++)
+    for (int j = 0; j <= i; j++) { cov[i][j] = cov[j][i] = S2[t] / W - m[i] * m[j]; t++; }
+  for (int i = 0; i < k; i++) {
+    var[i] = cov[i][i];
+    Rq[i] = E[i] / (W * beta);
+    lam[i] = Rq[i] / var[i];
+    cvec[i] = i;
+  }
+  if (sort) {   // ascending, stable insertion sort (np.argsort order for distinct values)
+    for (int i = 1; i < k; i++) {
+      const int c = cvec[i]; int j = i - 1;
+      while (j >= 0 && lam[cvec[j]] > lam[c]) { cvec[j + 1] = cvec[j]; j--; }
+      cvec[j + 1] = c;
+    }
+  }
+  for (int p = 0; p < k; p++) wt[cvec[p]] = eigw.v[p];
+  double nonpen = 0.0, pen = 0.0;
+  for (int i = 0; i < k; i++) { nonpen += wt[i] * lam[i]; pen += (var[i] - 1.0) * (var[i] - 1.0); }
+  for (int i = 0; i < k; i++)
+    for (int j = i + 1; j < k; j++) pen += cov[i][j] * cov[i][j];
+  out[EPDE_OUT_LOSS] = nonpen + alpha * pen;
+  out[EPDE_OUT_NONPEN] = nonpen;
+  out[EPDE_OUT_PENALTY] = pen;
+  out[EPDE_OUT_TOTW] = W;
+  for (int p = 0; p < k; p++) {
+    out[EPDE_OUT_EIG(k) + p] = lam[cvec[p]];
+    out[EPDE_OUT_CVEC(k) + p] = (double)cvec[p];
+    out[EPDE_OUT_MEAN(k) + p] = m[p];
+    out[EPDE_OUT_VAR(k) + p] = var[p];
+  }
+  if (coef) {
+    for (int i = 0; i < k; i++) {
+      coef->ecoef[i] = (float)(wt[i] / (W * beta * var[i]));
+      double cmi = 0.0;
+      for (int j = 0; j < k; j++) {
+        const double c = (i == j) ? 2.0 * (-wt[i] * Rq[i] / (var[i] * var[i]) + 2.0 * alpha * (var[i] - 1.0))
+                                  : 2.0 * alpha * cov[i][j];
+        coef->Cw[i][j] = (float)(c / W);
+        cmi += c / W * m[j];
+      }
+      coef->cm[i] = (float)cmi;
+    }
+  }
+}
+
+template <int K>
+cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* X, const float* w, const int64_t* idx,
+                         int64_t B, int d_pad, const float* pw, float* ybuf, double* part) {
+  cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(X, w, idx, B, d_pad, pw, ybuf, part);
+  return cudaGetLastError();
+}
+
+int fused_partial(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                  const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
+  FusedWs W = fused_ws(D, B, ws);
+  int nsm; int rc = sm_count(&nsm); if (rc) return rc;
+  k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
+  const int64_t npairs = (B + 1) / 2;
+  int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
+  if (grid > nsm) grid = nsm;
+  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
+  cudaError_t e;
+  switch (D->k) {
+    case 1: e = launch_pass1<1>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 2: e = launch_pass1<2>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 3: e = launch_pass1<3>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 4: e = launch_pass1<4>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 5: e = launch_pass1<5>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    default: e = launch_pass1<6>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+  }
+  if (e != cudaSuccess) return (int)e;
+  k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums);
+  return (int)cudaGetLastError();
+}
+
+int fused_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                 const float* params, const float* diag, double beta, double alpha, const EigW& ew,
+                 const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
+  FusedWs W = fused_ws(D, B, ws);
+  int nsm; int rc = sm_count(&nsm); if (rc) return rc;
+  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
+  const int64_t ntiles = (B + P2_T - 1) / P2_T;
+  int gx = nsm / D->k; if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = (int)ntiles;
+  const size_t smem = pass2_smem_bytes<kFusedH>(D->d, D->d_pad);
+  cudaError_t e = cudaFuncSetAttribute(k_pass2<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(X, w, idx, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
+                                                              W.coef, W.pg);
+  e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
+  const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
+  k_fin2<kFusedH><<<D->k, 512, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+  return (int)cudaGetLastError();
+}
+
+int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, const float* params,
+                 const float* diag, void* ws, size_t ws_bytes) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!X || !w || !params || !diag || !ws) return EPDE_ERR_NULL;
+  if (B < 1) return EPDE_ERR_ARG;
+  if (((uintptr_t)X & 15) || ((uintptr_t)ws & 255)) return EPDE_ERR_ALIGN;
+  size_t need; rc = epde_workspace_bytes(D, B, &need); if (rc) return rc;
+  if (ws_bytes < need) return EPDE_ERR_WORKSPACE;
+  return EPDE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int epde_abi_version(void) { return EPDE_ABI_VERSION; }
+
+const char* epde_error_string(int code) {
+  switch (code) {
+    case EPDE_OK: return "ok";
+    case EPDE_ERR_NULL: return "required pointer is NULL";
+    case EPDE_ERR_DESC: return "malformed descriptor";
+    case EPDE_ERR_UNSUPPORTED: return "configuration not supported by this build";
+    case EPDE_ERR_WORKSPACE: return "workspace too small";
+    case EPDE_ERR_ALIGN: return "pointer or stride alignment";
+    case EPDE_ERR_ARG: return "invalid argument";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int epde_param_count(const epde_desc* D, int64_t* out) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!out) return EPDE_ERR_NULL;
+  *out = param_count(D);
+  return EPDE_OK;
+}
+
+int epde_num_sums(const epde_desc* D, int32_t* out) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!out) return EPDE_ERR_NULL;
+  *out = num_sums(D->k);
+  return EPDE_OK;
+}
+
+int epde_has_fused_path(const epde_desc* D) {
+  int rc = check_desc(D); if (rc) return rc;
+  return fused_ok(D) ? 1 : 0;
+}
+
+int epde_workspace_bytes(const epde_desc* D, int64_t B, size_t* out) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!out) return EPDE_ERR_NULL;
+  if (B < 1) return EPDE_ERR_ARG;
+  // + kSumsTail bytes at the end: scratch for the sums of the single-call epde_step
+  if (fused_ok(D)) { *out = fused_ws(D, B, nullptr).total + kSumsTail; return EPDE_OK; }
+  rc = generic_workspace_bytes(D, B, out);
+  if (rc == EPDE_OK) *out = align_up(*out, 256) + kSumsTail;
+  return rc;
+}
+
+int epde_step_partial(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                      const float* params, const float* diag, void* ws, size_t ws_bytes, double* sums,
+                      void* stream) {
+  int rc = check_common(D, X, w, B, params, diag, ws, ws_bytes); if (rc) return rc;
+  if (!sums) return EPDE_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused_ok(D)) return fused_partial(D, X, w, idx, B, params, diag, ws, sums, st);
+  return generic_partial(D, X, w, idx, B, params, diag, ws, sums, st);
+}
+
+int epde_step_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                     const float* params, const float* diag, double beta, double alpha, const double* h_eig_w,
+                     const double* sums, void* ws, size_t ws_bytes, double* out, float* grad, void* stream) {
+  int rc = check_common(D, X, w, B, params, diag, ws, ws_bytes); if (rc) return rc;
+  if (!h_eig_w || !sums || !out || !grad) return EPDE_ERR_NULL;
+  EigW ew; memset(&ew, 0, sizeof(ew));
+  for (int i = 0; i < D->k; i++) ew.v[i] = h_eig_w[i];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fused_ok(D)) return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, st);
+  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, nullptr);
+  return generic_finish(D, X, w, idx, B, params, diag, beta, alpha, ew.v, sums, ws, out, grad, st);
+}
+
+int epde_step(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+              const float* params, const float* diag, double beta, double alpha, const double* h_eig_w,
+              void* ws, size_t ws_bytes, double* out, float* grad, void* stream) {
+  int rc = check_common(D, X, w, B, params, diag, ws, ws_bytes); if (rc) return rc;
+  if (!out) return EPDE_ERR_NULL;
+  size_t need; epde_workspace_bytes(D, B, &need);
+  double* sums = (double*)((char*)ws + need - kSumsTail);
+  rc = epde_step_partial(D, X, w, idx, B, params, diag, ws, ws_bytes, sums, stream); if (rc) return rc;
+  return epde_step_finish(D, X, w, idx, B, params, diag, beta, alpha, h_eig_w, sums, ws, ws_bytes, out, grad, stream);
+}
+
+int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t B, const float* params,
+                 const float* diag, void* ws, size_t ws_bytes, float* y, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!X || !params || !y || !ws || !diag) return EPDE_ERR_NULL;
+  if (B < 1) return EPDE_ERR_ARG;
+  if (((uintptr_t)X & 15) || ((uintptr_t)ws & 255)) return EPDE_ERR_ALIGN;
+  size_t need; rc = epde_workspace_bytes(D, 1, &need); if (rc) return rc;
+  if (ws_bytes < need) return EPDE_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!fused_ok(D)) return generic_forward(D, X, idx, B, params, ws, y, st);
+  FusedWs W = fused_ws(D, 1, ws);
+  int nsm; rc = sm_count(&nsm); if (rc) return rc;
+  k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
+  const int64_t npairs = (B + 1) / 2;
+  int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
+  if (grid > 4 * nsm) grid = 4 * nsm;
+  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_forward<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_forward<kFusedH><<<grid, P1_THREADS, smem, st>>>(X, idx, B, D->d_pad, D->k, W.pw, y);
+  return (int)cudaGetLastError();
+}
+
+// ---- host-side MT19937 (CPython `random` compatible) ----------------------------------------
+static void mt_twist(uint32_t* mt) {
+  const int N = 624, M = 397;
+  for (int kk = 0; kk < N; kk++) {
+    const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % N] & 0x7fffffffu);
+    mt[kk] = mt[(kk + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+}
+static inline uint32_t mt_next(uint32_t* mt, int32_t* pos) {
+  if (*pos >= 624) { mt_twist(mt); *pos = 0; }
+  uint32_t y = mt[(*pos)++];
+  y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+  return y;
+}
+
+int epde_minibatch_indices(uint32_t* mt, int32_t* pos, int64_t K, int64_t B, int64_t* out) {
+  if (!mt || !pos || !out) return EPDE_ERR_NULL;
+  if (K < 1 || B < 0 || *pos < 0 || *pos > 624) return EPDE_ERR_ARG;
+  const double total = (double)K;
+  for (int64_t i = 0; i < B; i++) {
+    const uint32_t a = mt_next(mt, pos) >> 5, b = mt_next(mt, pos) >> 6;
+    const double u = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    int64_t j = (int64_t)floor(u * total);     // bisect over cum_weights = 1..K (src/data_set.py:31,67)
+    if (j > K - 1) j = K - 1;
+    out[i] = j;
+  }
+  return EPDE_OK;
+}
+
+int epde_mt_seed(const uint32_t* key, int32_t key_len, uint32_t* mt, int32_t* pos) {
+  if (!key || !mt || !pos) return EPDE_ERR_NULL;
+  if (key_len < 1) return EPDE_ERR_ARG;
+  const int N = 624;
+  mt[0] = 19650218u;
+  for (int i = 1; i < N; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+  int i = 1, j = 0;
+  for (int kk = (N > key_len ? N : key_len); kk; kk--) {
+    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+    i++; j++;
+    if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+    if (j >= key_len) j = 0;
+  }
+  for (int kk = N - 1; kk; kk--) {
+    mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+    i++;
+    if (i >= N) { mt[0] = mt[N - 1]; i = 1; }
+  }
+  mt[0] = 0x80000000u;
+  *pos = N;
+  return EPDE_OK;
+}
+
+// ---- fused Adam -----------------------------------------------------------------------------
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, int64_t n, float lr, float bc1, float bc2_sqrt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = 0.9f * m[i] + 0.1f * gi;
+  const float vi = 0.999f * v[i] + 0.001f * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + 1e-8f;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+int epde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, int64_t step, void* stream) {
+  if (!p || !g || !m || !v) return EPDE_ERR_NULL;
+  if (n < 1 || step < 1) return EPDE_ERR_ARG;
+  const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, (float)bc1,
+                                                                         (float)sqrt(bc2));
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Shared device helpers for the EigenPDE-NN step kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace epde {
+
+// ---- packed FP32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2) ---------------------------
+// fma.rn.f32x2 issues ONE instruction for two FP32 FMAs; ptxas folds a {w,w} splat operand
+// into the scalar-broadcast form (FFMA2 Rd, Rw.F32, Rx.F32x2, Rc.F32x2), which is how the
+// broadcast weights enter the per-sample mat-vecs below.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 splat(float w) { return make_float2(w, w); }
+
+// ---- tanh ----------------------------------------------------------------------------------
+// EPDE_FAST_TANH: 1 - 2/(exp2(2x log2 e) + 1) with MUFU.EX2 + MUFU.RCP (abs. error ~2e-7);
+// otherwise CUDA's tanhf (<= 2 ulp).  Both are MUFU-bound (2 MUFU per value).
+__device__ __forceinline__ float tanh1(float x) {
+#ifdef EPDE_FAST_TANH
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+#else
+  return tanhf(x);
+#endif
+}
+__device__ __forceinline__ float2 tanh2(float2 z) { return make_float2(tanh1(z.x), tanh1(z.y)); }
+
+// y[o] += sum_i W[i][o] * x[i] for a sample pair; W in shared memory, row i contiguous over o
+// (16-byte aligned rows).  One broadcast LDS.128 feeds four FFMA2.
+template <int NIN, int NOUT>
+__device__ __forceinline__ void mv_acc(const float* __restrict__ sW, const float2 (&x)[NIN], float2 (&y)[NOUT]) {
+  static_assert(NOUT % 4 == 0, "row length must be a multiple of 4");
+#pragma unroll
+  for (int i = 0; i < NIN; i++) {
+#pragma unroll
+    for (int q = 0; q < NOUT / 4; q++) {
+      const float4 w = *reinterpret_cast<const float4*>(sW + i * NOUT + 4 * q);
+      y[4 * q + 0] = ffma2(splat(w.x), x[i], y[4 * q + 0]);
+      y[4 * q + 1] = ffma2(splat(w.y), x[i], y[4 * q + 1]);
+      y[4 * q + 2] = ffma2(splat(w.z), x[i], y[4 * q + 2]);
+      y[4 * q + 3] = ffma2(splat(w.w), x[i], y[4 * q + 3]);
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void zero2(float2 (&y)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++) y[i] = make_float2(0.f, 0.f);
+}
+
+// y[o] = {b[o], b[o]} from a shared-memory bias vector
+template <int N>
+__device__ __forceinline__ void bias2(const float* __restrict__ sb, float2 (&y)[N]) {
+#pragma unroll
+  for (int q = 0; q < N / 4; q++) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    y[4 * q + 0] = splat(b.x); y[4 * q + 1] = splat(b.y);
+    y[4 * q + 2] = splat(b.z); y[4 * q + 3] = splat(b.w);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace epde

@@ -1,0 +1,654 @@
+// Fused FFMA2 kernel family for nets  d -> H -> H -> H -> 1  with Tanh (the shape of both
+// shipped examples, arch_size_list = 20,20,20).  See DESIGN.md "Kernels" for the derivation.
+//
+//   k_pack   : flat parameters -> per-net packed shared-memory image (+ K = W1 diag(c) W1^T)
+//   k_pass1  : forward + input-Jacobian chain + energy -> per-CTA fp64 partial sums, y[B][k]
+//   k_pass2  : recompute forward/Jacobian, reverse sweeps, weight-gradient outer products
+//   k_fin2   : fixed-order fp64 reduction of the per-CTA gradient partials -> flat gradient
+//
+// Thread = one PAIR of samples (the two lanes of every FFMA2); weights are broadcast from
+// shared memory (one LDS.128 per four FFMA2).
+#pragma once
+#include "epde_common.cuh"
+
+namespace epde {
+
+// ---- packed per-net weight image (floats) ---------------------------------------------------
+template <int H>
+struct PackLayout {
+  int d_pad;
+  __host__ __device__ explicit PackLayout(int dp) : d_pad(dp) {}
+  __host__ __device__ int W1c() const { return 0; }                 // [d_pad/4][H][4]: W1[o][4*j4+q]
+  __host__ __device__ int b1() const { return d_pad * H; }
+  __host__ __device__ int W2T() const { return b1() + H; }          // [i][o] = W2[o][i]
+  __host__ __device__ int W2() const { return W2T() + H * H; }      // [o][i]
+  __host__ __device__ int b2() const { return W2() + H * H; }
+  __host__ __device__ int W3T() const { return b2() + H; }
+  __host__ __device__ int W3() const { return W3T() + H * H; }
+  __host__ __device__ int b3() const { return W3() + H * H; }
+  __host__ __device__ int w4() const { return b3() + H; }
+  __host__ __device__ int b4() const { return w4() + H; }           // 4 floats, [0] used
+  __host__ __device__ int Km() const { return b4() + 4; }           // [H][H] symmetric
+  __host__ __device__ int total() const { return Km() + H * H; }
+};
+
+// ---- per-net gradient accumulator image (floats) --------------------------------------------
+template <int H>
+struct GradLayout {
+  int d_pad;
+  __host__ __device__ explicit GradLayout(int dp) : d_pad(dp) {}
+  __host__ __device__ int gW1() const { return 0; }                 // [H][d_pad]  (z-part only)
+  __host__ __device__ int gb1() const { return H * d_pad; }
+  __host__ __device__ int gW2() const { return gb1() + H; }         // [H][H]
+  __host__ __device__ int gb2() const { return gW2() + H * H; }
+  __host__ __device__ int gW3() const { return gb2() + H; }
+  __host__ __device__ int gb3() const { return gW3() + H * H; }
+  __host__ __device__ int gw4() const { return gb3() + H; }
+  __host__ __device__ int gb4() const { return gw4() + H; }         // 4 floats, [0] used
+  __host__ __device__ int Gam() const { return gb4() + 4; }         // [H][H] = sum ebar g1 g1^T
+  __host__ __device__ int total() const { return Gam() + H * H; }
+};
+
+// flat (model.parameters()) size of one net
+template <int H>
+__host__ __device__ inline int flat_net_size(int d) { return H * d + H + 2 * (H * H + H) + H + 1; }
+
+// ---------------------------------------------------------------------------------------------
+// k_pack: one CTA per net
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void k_pack(const float* __restrict__ params, const float* __restrict__ diag_coeff, int d, int d_pad,
+                       float* __restrict__ pw) {
+  const PackLayout<H> L(d_pad);
+  const int net = blockIdx.x;
+  const float* p = params + (size_t)net * flat_net_size<H>(d);
+  float* o = pw + (size_t)net * L.total();
+  const float* W1 = p;
+  const float* b1 = W1 + H * d;
+  const float* W2 = b1 + H;
+  const float* b2 = W2 + H * H;
+  const float* W3 = b2 + H;
+  const float* b3 = W3 + H * H;
+  const float* W4 = b3 + H;
+  const float* b4 = W4 + H;
+  for (int e = threadIdx.x; e < d_pad * H; e += blockDim.x) {
+    const int q = e & 3, oo = (e >> 2) % H, j4 = (e >> 2) / H, j = 4 * j4 + q;
+    o[L.W1c() + e] = (j < d) ? W1[oo * d + j] : 0.f;
+  }
+  for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
+    const int a = e / H, b = e % H;
+    o[L.W2T() + e] = W2[b * H + a];
+    o[L.W2() + e] = W2[e];
+    o[L.W3T() + e] = W3[b * H + a];
+    o[L.W3() + e] = W3[e];
+    double s = 0.0;
+    for (int j = 0; j < d; j++) s += (double)diag_coeff[j] * (double)W1[a * d + j] * (double)W1[b * d + j];
+    o[L.Km() + e] = (float)s;
+  }
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
+    o[L.b1() + e] = b1[e]; o[L.b2() + e] = b2[e]; o[L.b3() + e] = b3[e]; o[L.w4() + e] = W4[e];
+  }
+  if (threadIdx.x < 4) o[L.b4() + threadIdx.x] = (threadIdx.x == 0) ? b4[0] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared pieces of the per-sample-pair computation
+// ---------------------------------------------------------------------------------------------
+// layer 1: z1 = W1 x + b1 with x read straight from the (gathered) global rows.  FFMA2 lanes
+// pair neighbouring input columns here (natural register pairs of the float4 row loads); the
+// two partial sums are added at the end.  a1 = tanh(z1) as a sample pair.
+template <int H>
+__device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1c, const float* __restrict__ sb1,
+                                           const float* __restrict__ xr0, const float* __restrict__ xr1, int nj4,
+                                           float2 (&a1)[H]) {
+  float2 s0[H], s1[H];
+  zero2(s0); zero2(s1);
+#pragma unroll 1
+  for (int j4 = 0; j4 < nj4; j4++) {
+    const float4 xa = __ldg(reinterpret_cast<const float4*>(xr0) + j4);
+    const float4 xb = __ldg(reinterpret_cast<const float4*>(xr1) + j4);
+    const float* wrow = sW1c + j4 * (H * 4);
+#pragma unroll
+    for (int o = 0; o < H; o++) {
+      const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o);
+      s0[o] = ffma2(make_float2(w.x, w.y), make_float2(xa.x, xa.y), s0[o]);
+      s1[o] = ffma2(make_float2(w.x, w.y), make_float2(xb.x, xb.y), s1[o]);
+      s0[o] = ffma2(make_float2(w.z, w.w), make_float2(xa.z, xa.w), s0[o]);
+      s1[o] = ffma2(make_float2(w.z, w.w), make_float2(xb.z, xb.w), s1[o]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < H / 4; q++) {
+    const float4 b = *reinterpret_cast<const float4*>(sb1 + 4 * q);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int o = 4 * q + r;
+      a1[o] = tanh2(make_float2(s0[o].x + s0[o].y + bb[r], s1[o].x + s1[o].y + bb[r]));
+    }
+  }
+}
+
+// hidden layer: a_out = tanh(W a_in + b), weights in [in][out] layout
+template <int H>
+__device__ __forceinline__ void fwd_hidden(const float* __restrict__ sWT, const float* __restrict__ sb,
+                                           const float2 (&ain)[H], float2 (&aout)[H]) {
+  bias2<H>(sb, aout);
+  mv_acc<H, H>(sWT, ain, aout);
+#pragma unroll
+  for (int o = 0; o < H; o++) aout[o] = tanh2(aout[o]);
+}
+
+// y = b4 + w4 . a3
+template <int H>
+__device__ __forceinline__ float2 fwd_out(const float* __restrict__ sw4, const float* __restrict__ sb4,
+                                          const float2 (&a3)[H]) {
+  float2 y0 = splat(sb4[0]), y1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < H / 4; q++) {
+    const float4 w = *reinterpret_cast<const float4*>(sw4 + 4 * q);
+    y0 = ffma2(splat(w.x), a3[4 * q + 0], y0);
+    y1 = ffma2(splat(w.y), a3[4 * q + 1], y1);
+    y0 = ffma2(splat(w.z), a3[4 * q + 2], y0);
+    y1 = ffma2(splat(w.w), a3[4 * q + 3], y1);
+  }
+  return fadd2(y0, y1);
+}
+
+// g = (1 - a^2) * u   (tanh': phi'(z) = 1 - a^2)
+template <int H>
+__device__ __forceinline__ void dtanh_mul(const float2 (&a)[H], const float2 (&u)[H], float2 (&g)[H]) {
+#pragma unroll
+  for (int o = 0; o < H; o++) {
+    const float2 d = ffma2(make_float2(-a[o].x, -a[o].y), a[o], splat(1.0f));
+    g[o] = fmul2(d, u[o]);
+  }
+}
+
+// g3 = (1 - a3^2) * w4
+template <int H>
+__device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const float2 (&a3)[H], float2 (&g3)[H]) {
+#pragma unroll
+  for (int q = 0; q < H / 4; q++) {
+    const float4 w = *reinterpret_cast<const float4*>(sw4 + 4 * q);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int o = 4 * q + r;
+      const float2 d = ffma2(make_float2(-a3[o].x, -a3[o].y), a3[o], splat(1.0f));
+      g3[o] = fmul2(d, splat(ww[r]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pass1
+// ---------------------------------------------------------------------------------------------
+constexpr int P1_THREADS = 256;
+
+template <int H, int K>
+__global__ void __launch_bounds__(P1_THREADS, 1)
+k_pass1(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+        int d_pad, const float* __restrict__ pw, float* __restrict__ ybuf, double* __restrict__ part) {
+  constexpr int NS = 1 + 2 * K + K * (K + 1) / 2;
+  extern __shared__ float4 smem4[];
+  float* sw = reinterpret_cast<float*>(smem4);
+  const PackLayout<H> L(d_pad);
+  const int pwn = L.total();
+  for (int i = threadIdx.x; i < K * pwn; i += P1_THREADS) sw[i] = pw[i];
+  __syncthreads();
+
+  double acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) acc[s] = 0.0;
+
+  const int64_t npairs = (B + 1) >> 1;
+  const int nj4 = d_pad >> 2;
+  for (int64_t p = (int64_t)blockIdx.x * P1_THREADS + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * P1_THREADS) {
+    const int64_t n0 = 2 * p, n1 = 2 * p + 1;
+    const bool v1 = n1 < B;
+    const int64_t r0 = idx ? idx[n0] : n0;
+    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
+    const float w0 = w[r0], w1 = v1 ? w[r1] : 0.f;
+    const float* xr0 = X + r0 * d_pad;
+    const float* xr1 = X + r1 * d_pad;
+    float2 yv[K], ev[K];
+#pragma unroll 1
+    for (int net = 0; net < K; net++) {
+      const float* s = sw + net * pwn;
+      float2 a1[H], a2[H], a3[H], g[H], u[H];
+      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xr0, xr1, nj4, a1);
+      fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
+      fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a3);
+      const float2 y = fwd_out<H>(s + L.w4(), s + L.b4(), a3);
+      jac_top<H>(s + L.w4(), a3, g);                    // g3
+      zero2(u); mv_acc<H, H>(s + L.W3(), g, u);         // u2 = W3^T g3
+      dtanh_mul<H>(a2, u, g);                           // g2
+      zero2(u); mv_acc<H, H>(s + L.W2(), g, u);         // u1 = W2^T g2
+      dtanh_mul<H>(a1, u, g);                           // g1
+      zero2(u); mv_acc<H, H>(s + L.Km(), g, u);         // t = K g1
+      float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < H; o += 2) { e0 = ffma2(g[o], u[o], e0); e1 = ffma2(g[o + 1], u[o + 1], e1); }
+      const float2 e = fadd2(e0, e1);                   // sum_j c_j (d_j f)^2 = g1^T K g1
+      ybuf[n0 * K + net] = y.x;
+      if (v1) ybuf[n1 * K + net] = y.y;
+#pragma unroll
+      for (int q = 0; q < K; q++) if (q == net) { yv[q] = y; ev[q] = e; }
+    }
+    // fp64 accumulation of the batch sums
+    acc[0] += (double)w0 + (double)w1;
+    int s2 = 1 + 2 * K;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      const float wy0 = w0 * yv[i].x, wy1 = w1 * yv[i].y;
+      acc[1 + i] += (double)wy0 + (double)wy1;
+      acc[1 + K + i] += (double)(w0 * ev[i].x) + (double)(w1 * ev[i].y);
+#pragma unroll
+      for (int j = 0; j <= i; j++) { acc[s2] += (double)(wy0 * yv[j].x) + (double)(wy1 * yv[j].y); s2++; }
+    }
+  }
+  // block reduction in a fixed order
+  __shared__ double red[P1_THREADS / 32][NS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    const double v = warp_sum(acc[s]);
+    if (lane == 0) red[wid][s] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double v = 0.0;
+    for (int q = 0; q < P1_THREADS / 32; q++) v += red[q][threadIdx.x];
+    part[(size_t)blockIdx.x * NS + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pass2
+// ---------------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 128;            // 4 warps, one per SM sub-partition
+constexpr int P2_T = 2 * P2_THREADS;       // samples per tile
+constexpr int P2_TS = P2_T + 4;            // row stride (floats): rows start 4 banks apart
+constexpr int P2_NG = 2;                   // sample groups of the outer-product phases
+
+// shared-memory row map (rows of P2_TS floats, [feature][sample])
+template <int H>
+struct RowMap {
+  int xr;   // rows reserved for the transposed x tile = 5 * ceil(d / 5)
+  __host__ __device__ explicit RowMap(int d) : xr(5 * ((d + 4) / 5)) {}
+  // region 1
+  __host__ __device__ int A1() const { return 0; }
+  __host__ __device__ int A2() const { return H; }
+  __host__ __device__ int A3() const { return 2 * H; }      // later Z3
+  __host__ __device__ int Z3() const { return 2 * H; }
+  // region 2 (phase 1 use)
+  __host__ __device__ int R2() const { return 3 * H; }
+  __host__ __device__ int G3() const { return R2(); }
+  __host__ __device__ int G2() const { return R2() + H; }
+  __host__ __device__ int G1() const { return R2() + 2 * H; }
+  __host__ __device__ int xtop() const { return xr > 3 * H ? xr : 3 * H; }
+  __host__ __device__ int U1() const { return R2() + xtop(); }
+  __host__ __device__ int U2() const { return U1() + H; }
+  __host__ __device__ int EB() const { return U2() + H; }
+  // region 2 (phase 2 use): X over the G rows, Z2/Z1 over U1/U2
+  __host__ __device__ int XT() const { return R2(); }
+  __host__ __device__ int Z2() const { return U1(); }
+  __host__ __device__ int Z1() const { return U2(); }
+  // region 3: rows whose sums are gw4 / gb4
+  __host__ __device__ int S4() const { return EB() + 1; }
+  __host__ __device__ int YB() const { return S4() + H; }
+  __host__ __device__ int total() const { return YB() + 1; }
+};
+
+struct Coef {                      // written by k_coef, read by k_pass2
+  float ecoef[8];                  // ebar_{n,i} = w_n * ecoef[i]
+  float cm[8];                     // ybar_{n,i} = w_n * (sum_j Cw[i][j] y_{n,j} - cm[i])
+  float Cw[8][8];
+};
+
+template <int H>
+__host__ __device__ inline size_t pass2_smem_bytes(int d, int d_pad) {
+  return (size_t)RowMap<H>(d).total() * P2_TS * 4 + (size_t)PackLayout<H>(d_pad).total() * 4 +
+         (size_t)P2_NG * GradLayout<H>(d_pad).total() * 4;
+}
+
+// one 4x5 register tile of an outer product over the samples [n0, n0 + cnt):
+//   out[o][i] += sum_n P[o][n] * Q[i][n],  o in {ot + 5a}, i in {5*it + b}
+// FFMA2 lanes pair neighbouring samples; the two partial sums are added at the end.
+template <bool SCALE>
+__device__ __forceinline__ void outer_unit(const float* __restrict__ prow, const float* __restrict__ qrow,
+                                           const float* __restrict__ eb, int n0, int cnt,
+                                           float* __restrict__ out, int ld, int ot, int it, int imax) {
+  float2 acc[4][5];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 5; b++) acc[a][b] = make_float2(0.f, 0.f);
+  const float* p0 = prow + ot * P2_TS + n0;
+  const float* q0 = qrow + (5 * it) * P2_TS + n0;
+#pragma unroll 2
+  for (int n = 0; n < cnt; n += 4) {
+    float4 pv[4], qv[5];
+#pragma unroll
+    for (int a = 0; a < 4; a++) pv[a] = *reinterpret_cast<const float4*>(p0 + (5 * a) * P2_TS + n);
+#pragma unroll
+    for (int b = 0; b < 5; b++) qv[b] = *reinterpret_cast<const float4*>(q0 + b * P2_TS + n);
+    if (SCALE) {
+      const float4 s = *reinterpret_cast<const float4*>(eb + n0 + n);
+#pragma unroll
+      for (int a = 0; a < 4; a++) { pv[a].x *= s.x; pv[a].y *= s.y; pv[a].z *= s.z; pv[a].w *= s.w; }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 5; b++) {
+        acc[a][b] = ffma2(make_float2(pv[a].x, pv[a].y), make_float2(qv[b].x, qv[b].y), acc[a][b]);
+        acc[a][b] = ffma2(make_float2(pv[a].z, pv[a].w), make_float2(qv[b].z, qv[b].w), acc[a][b]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+      const int i = 5 * it + b;
+      if (i < imax) out[(ot + 5 * a) * ld + i] += acc[a][b].x + acc[a][b].y;
+    }
+}
+
+// sum of one row over the tile -> out
+__device__ __forceinline__ void row_sum(const float* __restrict__ row, float* __restrict__ out) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int n = 0; n < P2_T; n += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + n);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *out += (s.x + s.y) + (s.z + s.w);
+}
+
+template <int H>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+        int d, int d_pad, int K, const float* __restrict__ pw, const float* __restrict__ ybuf,
+        const Coef* __restrict__ coef, float* __restrict__ pg) {
+  static_assert(H % 5 == 0 && H % 4 == 0, "outer-product tiling assumes H multiple of 20");
+  extern __shared__ float4 smem4[];
+  const RowMap<H> R(d);
+  const PackLayout<H> L(d_pad);
+  const GradLayout<H> G(d_pad);
+  float* rows = reinterpret_cast<float*>(smem4);
+  float* sw = rows + (size_t)R.total() * P2_TS;
+  float* accS = sw + L.total();
+  const int gn = G.total();
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < L.total(); i += P2_THREADS) sw[i] = pw[(size_t)net * L.total() + i];
+  for (int i = tid; i < P2_NG * gn; i += P2_THREADS) accS[i] = 0.f;
+  const float ecoef = coef->ecoef[net];
+  const float cm = coef->cm[net];
+  float cw[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cw[j] = (j < K) ? coef->Cw[net][j] : 0.f;
+  __syncthreads();
+
+  const int col = 2 * tid;
+  const int nj4 = d_pad >> 2;
+  const int64_t ntiles = (B + P2_T - 1) / P2_T;
+#define ROW2(r) (*reinterpret_cast<float2*>(rows + (r) * P2_TS + col))
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t n0 = tile * P2_T + col, n1 = n0 + 1;
+    const bool v0 = n0 < B, v1 = n1 < B;
+    const int64_t r0 = v0 ? (idx ? idx[n0] : n0) : 0;
+    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
+    const float2 wn = make_float2(v0 ? w[r0] : 0.f, v1 ? w[r1] : 0.f);
+    const float* xr0 = X + r0 * d_pad;
+    const float* xr1 = X + r1 * d_pad;
+    float2 ze1[H], ze2[H];
+
+    // ================= MV1: forward, Jacobian chain, first reverse sweep ====================
+    {
+      float2 ybar;
+      {   // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
+        float s0 = -cm, s1 = -cm;
+        for (int j = 0; j < K; j++) {
+          s0 = fmaf(cw[j], v0 ? ybuf[n0 * K + j] : 0.f, s0);
+          s1 = fmaf(cw[j], v1 ? ybuf[n1 * K + j] : 0.f, s1);
+        }
+        ybar = make_float2(wn.x * s0, wn.y * s1);
+      }
+      const float2 ebar = make_float2(wn.x * ecoef, wn.y * ecoef);
+      float2 a[H], g[H], u[H];
+      fwd_layer1<H>(sw + L.W1c(), sw + L.b1(), xr0, xr1, nj4, a);
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.A1() + o) = a[o];
+      fwd_hidden<H>(sw + L.W2T(), sw + L.b2(), a, g);                  // g := a2
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.A2() + o) = g[o];
+      fwd_hidden<H>(sw + L.W3T(), sw + L.b3(), g, a);                  // a := a3
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.A3() + o) = a[o];
+      jac_top<H>(sw + L.w4(), a, g);                                   // g := g3
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.G3() + o) = g[o];
+      zero2(u); mv_acc<H, H>(sw + L.W3(), g, u);                       // u2 = W3^T g3
+#pragma unroll
+      for (int o = 0; o < H; o++) a[o] = ROW2(R.A2() + o);             // a := a2
+      dtanh_mul<H>(a, u, g);                                           // g := g2
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.G2() + o) = g[o];
+      zero2(u); mv_acc<H, H>(sw + L.W2(), g, u);                       // u1 = W2^T g2
+#pragma unroll
+      for (int o = 0; o < H; o++) a[o] = ROW2(R.A1() + o);             // a := a1
+      dtanh_mul<H>(a, u, g);                                           // g := g1
+#pragma unroll
+      for (int o = 0; o < H; o++) ROW2(R.G1() + o) = g[o];
+      ROW2(R.EB()) = ebar;
+      // ---- E-sweep, layer 1:  gbar1 = 2 ebar K g1
+      zero2(u); mv_acc<H, H>(sw + L.Km(), g, u);                       // t = K g1
+      const float2 e2 = make_float2(2.f * ebar.x, 2.f * ebar.y);
+#pragma unroll
+      for (int o = 0; o < H; o++) {
+        const float2 gb = fmul2(e2, u[o]);                             // gbar1
+        const float2 dd = ffma2(make_float2(-a[o].x, -a[o].y), a[o], splat(1.0f));
+        u[o] = fmul2(dd, gb);                                          // ubar1
+        ROW2(R.U1() + o) = u[o];
+        ze1[o] = fmul2(fmul2(make_float2(-2.f * a[o].x, -2.f * a[o].y), g[o]), gb);   // phi'' u1 gbar1
+      }
+      // ---- layer 2: gbar2 = W2 ubar1
+      zero2(g); mv_acc<H, H>(sw + L.W2T(), u, g);                      // g := gbar2
+#pragma unroll
+      for (int o = 0; o < H; o++) {
+        const float2 a2 = ROW2(R.A2() + o), g2 = ROW2(R.G2() + o);
+        const float2 dd = ffma2(make_float2(-a2.x, -a2.y), a2, splat(1.0f));
+        u[o] = fmul2(dd, g[o]);                                        // ubar2
+        ROW2(R.U2() + o) = u[o];
+        ze2[o] = fmul2(fmul2(make_float2(-2.f * a2.x, -2.f * a2.y), g2), g[o]);
+      }
+      // ---- layer 3: gbar3 = W3 ubar2
+      zero2(g); mv_acc<H, H>(sw + L.W3T(), u, g);                      // g := gbar3
+#pragma unroll
+      for (int o = 0; o < H; o++) {
+        const float2 a3 = ROW2(R.A3() + o), g3 = ROW2(R.G3() + o);
+        const float2 dd = ffma2(make_float2(-a3.x, -a3.y), a3, splat(1.0f));
+        const float2 ub3 = fmul2(dd, g[o]);                            // ubar3 -> d/d w4 (g_4 = 1)
+        ROW2(R.S4() + o) = ffma2(ybar, a3, ub3);                       // ubar3 + ybar a3
+        // zbar3 = phi'' u3 gbar3 + phi' w4 ybar = g3 (-2 a3 gbar3 + ybar)
+        const float2 t = ffma2(make_float2(-2.f * a3.x, -2.f * a3.y), g[o], ybar);
+        ROW2(R.Z3() + o) = fmul2(g3, t);
+      }
+      ROW2(R.YB()) = ybar;
+    }
+    __syncthreads();
+
+    // ================= GM1: Gamma, and the g (x) ubar parts of dW2, dW3 ======================
+    {
+      constexpr int UPJ = (H / 4) * (H / 5);     // 4x5 tiles of an H x H block
+      constexpr int NU = 3 * UPJ;
+      constexpr int SG = P2_T / P2_NG;
+      for (int wk = tid; wk < NU * P2_NG; wk += P2_THREADS) {
+        const int grp = wk / NU, un = wk % NU, job = un / UPJ, t = un % UPJ;
+        const int ot = t % 5, it = t / 5;
+        float* out = accS + grp * gn;
+        if (job == 0)
+          outer_unit<true>(rows + R.G1() * P2_TS, rows + R.G1() * P2_TS, rows + R.EB() * P2_TS, grp * SG, SG,
+                           out + G.Gam(), H, ot, it, H);
+        else if (job == 1)
+          outer_unit<false>(rows + R.G2() * P2_TS, rows + R.U1() * P2_TS, nullptr, grp * SG, SG,
+                            out + G.gW2(), H, ot, it, H);
+        else
+          outer_unit<false>(rows + R.G3() * P2_TS, rows + R.U2() * P2_TS, nullptr, grp * SG, SG,
+                            out + G.gW3(), H, ot, it, H);
+      }
+    }
+    __syncthreads();
+
+    // ================= MV2: second reverse sweep, x tile (transposed) ========================
+    {
+      float2 z[H], t[H];
+#pragma unroll
+      for (int o = 0; o < H; o++) z[o] = ROW2(R.Z3() + o);
+      zero2(t); mv_acc<H, H>(sw + L.W3(), z, t);                       // W3^T zbar3
+#pragma unroll
+      for (int o = 0; o < H; o++) {
+        const float2 a2 = ROW2(R.A2() + o);
+        const float2 dd = ffma2(make_float2(-a2.x, -a2.y), a2, splat(1.0f));
+        z[o] = ffma2(dd, t[o], ze2[o]);                                // zbar2
+        ROW2(R.Z2() + o) = z[o];
+      }
+      zero2(t); mv_acc<H, H>(sw + L.W2(), z, t);                       // W2^T zbar2
+#pragma unroll
+      for (int o = 0; o < H; o++) {
+        const float2 a1 = ROW2(R.A1() + o);
+        const float2 dd = ffma2(make_float2(-a1.x, -a1.y), a1, splat(1.0f));
+        ROW2(R.Z1() + o) = ffma2(dd, t[o], ze1[o]);                    // zbar1
+      }
+#pragma unroll 1
+      for (int j4 = 0; j4 < nj4; j4++) {
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(xr0) + j4);
+        const float4 xb = __ldg(reinterpret_cast<const float4*>(xr1) + j4);
+        const int j = 4 * j4;
+        if (j + 0 < R.xr) ROW2(R.XT() + j + 0) = make_float2(xa.x, xb.x);
+        if (j + 1 < R.xr) ROW2(R.XT() + j + 1) = make_float2(xa.y, xb.y);
+        if (j + 2 < R.xr) ROW2(R.XT() + j + 2) = make_float2(xa.z, xb.z);
+        if (j + 3 < R.xr) ROW2(R.XT() + j + 3) = make_float2(xa.w, xb.w);
+      }
+      for (int j = 4 * nj4; j < R.xr; j++) ROW2(R.XT() + j) = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    // ================= GM2: zbar (x) [x | a1 | a2], bias and w4 row sums =====================
+    {
+      constexpr int UPJ = (H / 4) * (H / 5);
+      const int njt = R.xr / 5;
+      const int nu1 = 5 * njt;                   // (H/4) * njt units for dW1
+      const int NU = nu1 + 2 * UPJ;
+      const int nrows = 4 * H + 1;
+      for (int wk = tid; wk < NU + nrows; wk += P2_THREADS) {
+        float* out = accS;                       // group 0 accumulates GM2
+        if (wk < nu1) {
+          outer_unit<false>(rows + R.Z1() * P2_TS, rows + R.XT() * P2_TS, nullptr, 0, P2_T,
+                            out + G.gW1(), d_pad, wk % 5, wk / 5, d);
+        } else if (wk < nu1 + UPJ) {
+          const int t = wk - nu1;
+          outer_unit<false>(rows + R.Z2() * P2_TS, rows + R.A1() * P2_TS, nullptr, 0, P2_T,
+                            out + G.gW2(), H, t % 5, t / 5, H);
+        } else if (wk < NU) {
+          const int t = wk - nu1 - UPJ;
+          outer_unit<false>(rows + R.Z3() * P2_TS, rows + R.A2() * P2_TS, nullptr, 0, P2_T,
+                            out + G.gW3(), H, t % 5, t / 5, H);
+        } else {
+          const int r = wk - NU;
+          float* o1 = accS + gn;                 // group 1 copy: no overlap with GM2 unit outputs
+          if (r < H) row_sum(rows + (R.Z1() + r) * P2_TS, o1 + G.gb1() + r);
+          else if (r < 2 * H) row_sum(rows + (R.Z2() + r - H) * P2_TS, o1 + G.gb2() + r - H);
+          else if (r < 3 * H) row_sum(rows + (R.Z3() + r - 2 * H) * P2_TS, o1 + G.gb3() + r - 2 * H);
+          else if (r < 4 * H) row_sum(rows + (R.S4() + r - 3 * H) * P2_TS, o1 + G.gw4() + r - 3 * H);
+          else row_sum(rows + R.YB() * P2_TS, o1 + G.gb4());
+        }
+      }
+    }
+    __syncthreads();
+  }
+#undef ROW2
+  float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;
+  for (int i = tid; i < gn; i += P2_THREADS) dst[i] = accS[i] + accS[gn + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fin2: one CTA per net; fixed-order fp64 reduction over the pass-2 CTAs, then
+//         dW1 += 2 Gamma W1 diag(c)   (the g1 (x) ubar_0 term, via u0 = W1^T g1)
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
+                       const float* __restrict__ params, const float* __restrict__ diag_coeff,
+                       float* __restrict__ grad) {
+  extern __shared__ double sred[];
+  const GradLayout<H> G(d_pad);
+  const int gn = G.total();
+  const int net = blockIdx.x;
+  for (int e = threadIdx.x; e < gn; e += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < ncta; c++) s += (double)pg[((size_t)c * K + net) * gn + e];
+    sred[e] = s;
+  }
+  __syncthreads();
+  const int fn = flat_net_size<H>(d);
+  const float* W1 = params + (size_t)net * fn;
+  float* g = grad + (size_t)net * fn;
+  for (int e = threadIdx.x; e < fn; e += blockDim.x) {
+    double v;
+    if (e < H * d) {
+      const int o = e / d, j = e % d;
+      double corr = 0.0;
+      for (int b = 0; b < H; b++) corr += sred[G.Gam() + o * H + b] * (double)W1[b * d + j];
+      v = sred[G.gW1() + o * d_pad + j] + 2.0 * (double)diag_coeff[j] * corr;
+    } else {
+      int r = e - H * d;
+      if (r < H) v = sred[G.gb1() + r];
+      else if ((r -= H) < H * H) v = sred[G.gW2() + r];
+      else if ((r -= H * H) < H) v = sred[G.gb2() + r];
+      else if ((r -= H) < H * H) v = sred[G.gW3() + r];
+      else if ((r -= H * H) < H) v = sred[G.gb3() + r];
+      else if ((r -= H) < H) v = sred[G.gw4() + r];
+      else v = sred[G.gb4()];
+    }
+    g[e] = (float)v;
+  }
+}
+
+// forward only: y[B][K]
+template <int H>
+__global__ void __launch_bounds__(P1_THREADS, 1)
+k_forward(const float* __restrict__ X, const int64_t* __restrict__ idx, int64_t B, int d_pad, int K,
+          const float* __restrict__ pw, float* __restrict__ y) {
+  extern __shared__ float4 smem4[];
+  float* sw = reinterpret_cast<float*>(smem4);
+  const PackLayout<H> L(d_pad);
+  const int pwn = L.total();
+  for (int i = threadIdx.x; i < K * pwn; i += P1_THREADS) sw[i] = pw[i];
+  __syncthreads();
+  const int64_t npairs = (B + 1) >> 1;
+  const int nj4 = d_pad >> 2;
+  for (int64_t p = (int64_t)blockIdx.x * P1_THREADS + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * P1_THREADS) {
+    const int64_t n0 = 2 * p, n1 = 2 * p + 1;
+    const bool v1 = n1 < B;
+    const int64_t r0 = idx ? idx[n0] : n0;
+    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
+#pragma unroll 1
+    for (int net = 0; net < K; net++) {
+      const float* s = sw + net * pwn;
+      float2 a1[H], a2[H];
+      fwd_layer1<H>(s + L.W1c(), s + L.b1(), X + r0 * d_pad, X + r1 * d_pad, nj4, a1);
+      fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
+      fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a1);
+      const float2 yy = fwd_out<H>(s + L.w4(), s + L.b4(), a1);
+      y[n0 * K + net] = yy.x;
+      if (v1) y[n1 * K + net] = yy.y;
+    }
+  }
+}
+
+}  // namespace epde

@@ -1,0 +1,167 @@
+"""Host side of the step: device mirrors, workspace, the autograd.Function.
+
+Mirrors the reference's interface for the hot path:
+  * `StepEngine.step(idx, params, alpha)` = the numerical content of
+    `eigen_solver.update_step` (src/pytorch_eigen_solver.py:191-236) up to and including
+    `loss.backward()`: returns eig_vals (ascending), cvec, loss, non_penalty_loss, penalty and the
+    flat parameter gradient.
+  * `EigenLossFn` exposes it as a `torch.autograd.Function` whose only differentiable output is
+    `loss`, so `optimizer.zero_grad(); loss.backward(); optimizer.step()` (:232-234) keeps working.
+
+PyTorch is used for device memory, streams and torch.distributed only; all arithmetic of the step
+runs in libeigenpde_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class StepEngine:
+    """Owns the fp32 device mirror of a data_set and runs loss+grad steps on it.
+
+    X: [K, d] array-like (fp64 as loaded by data_set.from_file), weights: [K].
+    arch: [d, n_1, ..., 1]; diag_coeff: [d] (src/pytorch_eigen_solver.py:76-81).
+    """
+
+    def __init__(self, X, weights, arch, k, activation_name, diag_coeff, beta, eig_w, sort=True,
+                 device=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise _lib.EpdeError("StepEngine needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.k = int(k)
+        self.arch = [int(a) for a in arch]
+        self.d = self.arch[0]
+        self.d_pad = (self.d + 3) // 4 * 4
+        self.beta = float(beta)
+        self.eig_w = [float(v) for v in eig_w][: self.k]
+        if len(self.eig_w) < self.k:
+            raise _lib.EpdeError("only %d weights for %d eigenvalues" % (len(self.eig_w), self.k))
+        self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort)
+        self.pg = process_group
+        n = C.c_int64()
+        _lib.check(self.lib.epde_param_count(C.byref(self.desc), C.byref(n)), "epde_param_count")
+        self.n_params = n.value
+        ns = C.c_int32()
+        _lib.check(self.lib.epde_num_sums(C.byref(self.desc), C.byref(ns)), "epde_num_sums")
+        self.n_sums = ns.value
+        self.fused = self.lib.epde_has_fused_path(C.byref(self.desc)) == 1
+        with torch.cuda.device(self.device):
+            Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+            self.K = Xt.shape[0]
+            self.X = torch.zeros((self.K, self.d_pad), dtype=torch.float32, device=self.device)
+            self.X[:, : self.d] = Xt.to(self.device)
+            self.w = torch.as_tensor(np.asarray(weights), dtype=torch.float32).to(self.device).contiguous()
+            self.diag = torch.as_tensor(np.asarray(diag_coeff), dtype=torch.float32).to(self.device).contiguous()
+            self.sums = torch.zeros(self.n_sums, dtype=torch.float64, device=self.device)
+            self.out = torch.zeros(4 + 4 * self.k, dtype=torch.float64, device=self.device)
+            self.grad = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self._ws = None
+        self._ws_B = 0
+        self._eigw_c = (C.c_double * self.k)(*self.eig_w)
+
+    # -- buffers ------------------------------------------------------------------------------
+    def _workspace(self, B):
+        if self._ws is None or B > self._ws_B:
+            need = C.c_size_t()
+            _lib.check(self.lib.epde_workspace_bytes(C.byref(self.desc), B, C.byref(need)), "epde_workspace_bytes")
+            self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
+            self._ws_B = B
+            off = (-self._ws.data_ptr()) % 256
+            self._ws_view = self._ws[off:off + need.value]
+        return self._ws_view
+
+    def flat_params(self, model) -> torch.Tensor:
+        """fp32 flat copy of model.parameters() (the reference keeps them in fp64, :374)."""
+        return torch.cat([p.detach().reshape(-1) for p in model.parameters()]).to(
+            device=self.device, dtype=torch.float32)
+
+    # -- the step -----------------------------------------------------------------------------
+    def step_device(self, idx_dev, B, params_dev, alpha):
+        """Asynchronous step on the current stream.  idx_dev: int64 device tensor or None.
+
+        Returns (out_scalars fp64 device tensor, grad fp32 device tensor), both owned by the engine.
+        With a process group the batch is the union of all ranks' idx slices.
+        """
+        ws = self._workspace(B)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        args = (C.byref(self.desc), _ptr(self.X), _ptr(self.w), _ptr(idx_dev), C.c_int64(B), _ptr(params_dev),
+                _ptr(self.diag))
+        if self.pg is None:
+            _lib.check(self.lib.epde_step(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                          _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), st),
+                       "epde_step")
+        else:
+            import torch.distributed as dist
+            _lib.check(self.lib.epde_step_partial(*args, _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.sums), st),
+                       "epde_step_partial")
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.pg)
+            _lib.check(self.lib.epde_step_finish(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                                 _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out),
+                                                 _ptr(self.grad), st), "epde_step_finish")
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        return self.out, self.grad
+
+    def step(self, idx, params_dev, alpha):
+        """Host-facing step: idx is a host int64 array/list (or None for rows 0..B-1 with B = K)."""
+        if idx is None:
+            idx_dev, B = None, self.K
+        else:
+            idx_t = torch.as_tensor(np.asarray(idx, dtype=np.int64))
+            B = idx_t.numel()
+            idx_dev = idx_t.to(self.device, non_blocking=True)
+        out, grad = self.step_device(idx_dev, B, params_dev, alpha)
+        h = out.cpu().numpy()
+        k = self.k
+        return dict(loss=h[0], non_penalty=h[1], penalty=h[2], tot_weight=h[3], eig_vals=h[4:4 + k].copy(),
+                    cvec=h[4 + k:4 + 2 * k].astype(np.int64), mean=h[4 + 2 * k:4 + 3 * k].copy(),
+                    var=h[4 + 3 * k:4 + 4 * k].copy(), grad=grad)
+
+    def forward(self, idx_dev, B, params_dev):
+        ws = self._workspace(max(B, 1))
+        y = torch.empty((B, self.k), dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.epde_forward(C.byref(self.desc), _ptr(self.X), _ptr(idx_dev), C.c_int64(B),
+                                         _ptr(params_dev), _ptr(self.diag), _ptr(ws), C.c_size_t(ws.numel()),
+                                         _ptr(y), st), "epde_forward")
+        return y
+
+
+class EigenLossFn(torch.autograd.Function):
+    """loss = EigenLossFn.apply(engine, idx, alpha, *model.parameters())
+
+    Forward runs the whole fused loss+gradient step and caches d loss / d theta; backward hands the
+    cached gradient (times grad_output) back to autograd as one view per parameter, in
+    model.parameters() order.  Non-differentiable results are left on `engine.last`.
+    """
+
+    @staticmethod
+    def forward(ctx, engine, idx, alpha, *params):
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).to(device=engine.device, dtype=torch.float32)
+        res = engine.step(idx, flat, float(alpha))
+        engine.last = res
+        ctx.shapes = [p.shape for p in params]
+        ctx.meta = (params[0].dtype, params[0].device)
+        ctx.save_for_backward(res["grad"].clone())
+        return torch.tensor(res["loss"], dtype=params[0].dtype, device=params[0].device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        dtype, device = ctx.meta
+        g = g.to(device=device, dtype=dtype) * grad_out.to(device=device, dtype=dtype)
+        outs, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            outs.append(g[off:off + n].view(shp))
+            off += n
+        return (None, None, None) + tuple(outs)

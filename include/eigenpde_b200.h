@@ -1,0 +1,168 @@
+/*
+ * eigenpde_b200.h -- C ABI of the B200 (sm_100a) loss+gradient step for EigenPDE-NN.
+ *
+ * The reference (zwpku/EigenPDE-NN) has no FFI/plugin interface: its hot path is the
+ * Python method eigen_solver.update_step (src/pytorch_eigen_solver.py:191-236) with the
+ * helpers fun_and_grad_on_data (:150-173) and penalty_term (:177-189).  This header is the
+ * boundary a replacement library exports for that path; every entry point names the
+ * reference lines it replaces.  Plain C: pointers and sizes only, no torch / C++ types.
+ *
+ * Conventions
+ *   - All pointers named d_* are DEVICE pointers (CUDA global memory); h_* are host pointers.
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); nothing in the
+ *     library synchronises the host.  One in-flight call per workspace.
+ *   - Return value: 0 = ok; negative = EPDE_ERR_* (argument / unsupported configuration);
+ *     positive = a cudaError_t reported by the runtime.  The library never aborts or throws.
+ *   - The library allocates nothing persistent: the caller owns every buffer and queries the
+ *     workspace size first.  No global mutable state; entry points are re-entrant.
+ *   - Parameters are one flat fp32 vector in `model.parameters()` order of the reference's
+ *     network_arch.MyNet (src/network_arch.py:25,90): for each net i = 0..k-1, for each
+ *     layer l = 1..L: W_l row-major [n_l][n_{l-1}], then b_l [n_l].  Gradients use the same
+ *     layout.
+ *   - Samples: X is the device mirror of data_set.X_vec (src/data_set.py:21) as fp32 with a
+ *     row stride of d_pad floats (d_pad % 4 == 0, X 16-byte aligned, padding = 0); `w` is
+ *     data_set.weights (src/data_set.py:22) as fp32; `idx` are the minibatch row indices of
+ *     data_set.generate_minibatch (src/data_set.py:67,77), or NULL for rows 0..B-1.
+ */
+#ifndef EIGENPDE_B200_H
+#define EIGENPDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPDE_ABI_VERSION 1
+#define EPDE_MAX_LAYERS 8   /* Linear layers per net */
+#define EPDE_MAX_K 8        /* eigenfunctions (nets) */
+
+/* activation ids: names accepted by the reference (src/network_arch.py:27-32, params.cfg:22) */
+enum {
+  EPDE_ACT_TANH = 0,
+  EPDE_ACT_SIGMOID = 1,
+  EPDE_ACT_SOFTPLUS = 2,
+  EPDE_ACT_LOGSIGMOID = 3,
+  EPDE_ACT_ELU = 4,       /* also CELU (alpha = 1), the reference's fallback */
+  EPDE_ACT_RELU = 5,
+  EPDE_ACT_TANHSHRINK = 6
+};
+
+enum {
+  EPDE_OK = 0,
+  EPDE_ERR_NULL = -1,         /* required pointer is NULL */
+  EPDE_ERR_DESC = -2,         /* malformed descriptor (sizes out of range) */
+  EPDE_ERR_UNSUPPORTED = -3,  /* valid descriptor the library has no kernel for */
+  EPDE_ERR_WORKSPACE = -4,    /* workspace too small */
+  EPDE_ERR_ALIGN = -5,        /* pointer / stride alignment */
+  EPDE_ERR_ARG = -6           /* other invalid argument (B <= 0, ...) */
+};
+
+#define EPDE_FLAG_SORT 1u     /* sort_eigvals_in_training (src/pytorch_eigen_solver.py:217-221) */
+
+typedef struct epde_desc {
+  int32_t d;                            /* input dimension n_0 (data_set.tot_dim) */
+  int32_t d_pad;                        /* row stride of X in floats */
+  int32_t k;                            /* number of nets / eigenfunctions */
+  int32_t n_layers;                     /* L = number of Linear layers (arch_list length - 1) */
+  int32_t widths[EPDE_MAX_LAYERS + 1];  /* n_0 .. n_L, n_L must be 1 (src/pytorch_eigen_solver.py:352) */
+  int32_t act_id;                       /* EPDE_ACT_* */
+  uint32_t flags;                       /* EPDE_FLAG_* */
+} epde_desc;
+
+/* out_scalars layout (fp64, device): what update_step returns at :236 plus the moments */
+#define EPDE_OUT_LOSS 0
+#define EPDE_OUT_NONPEN 1
+#define EPDE_OUT_PENALTY 2
+#define EPDE_OUT_TOTW 3
+#define EPDE_OUT_EIG(k) 4                 /* k sorted eigenvalue estimates */
+#define EPDE_OUT_CVEC(k) (4 + (k))        /* k permutation entries (stored as doubles) */
+#define EPDE_OUT_MEAN(k) (4 + 2 * (k))    /* k weighted means   (:172) */
+#define EPDE_OUT_VAR(k) (4 + 3 * (k))     /* k weighted variances (:173) */
+#define EPDE_OUT_COUNT(k) (4 + 4 * (k))
+
+int epde_abi_version(void);
+const char* epde_error_string(int code);
+
+/* number of parameters of all k nets (sum of p.numel(), src/pytorch_eigen_solver.py:382) */
+int epde_param_count(const epde_desc* desc, int64_t* out);
+
+/* number of batch-global partial sums exchanged between the two phases:
+ * [W, S1(k), E(k), S2(k(k+1)/2, row-major lower triangle)] -- the fp64 quantities behind
+ * src/pytorch_eigen_solver.py:169-173,215 and :186 */
+int epde_num_sums(const epde_desc* desc, int32_t* out);
+
+/* 1 if the fused FFMA2 kernel family covers this descriptor, 0 if the generic layer-wise
+ * kernels are used; negative on a malformed descriptor */
+int epde_has_fused_path(const epde_desc* desc);
+
+int epde_workspace_bytes(const epde_desc* desc, int64_t B, size_t* out);
+
+/*
+ * Phase 1 of update_step: forward of the k nets, input gradients and the batch sums.
+ * Replaces fun_and_grad_on_data (src/pytorch_eigen_solver.py:150-173: model forward :157,
+ * autograd.grad :164, weights :166-169) and the reductions of :215 and :186 for the
+ * samples of THIS rank.  Writes epde_num_sums() doubles to d_sums.
+ */
+int epde_step_partial(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx,
+                      int64_t B, const float* d_params, const float* d_diag_coeff,
+                      void* d_workspace, size_t workspace_bytes, double* d_sums, void* stream);
+
+/*
+ * Phase 2: given the batch-global sums (d_sums, after an allreduce when the batch is
+ * sharded), form eig_vals / cvec / non_penalty_loss / penalty / loss
+ * (src/pytorch_eigen_solver.py:215-229, 177-189) and back-propagate into the parameters
+ * (loss.backward(), :233) for the samples of THIS rank.  d_grad receives this rank's
+ * additive share of d loss / d theta (sum over ranks = full gradient).
+ * h_eig_w: k host doubles (Param.eig_w, only the first k are used, :224).
+ * Must be called with the same X/w/idx/B/params/workspace as the preceding epde_step_partial.
+ */
+int epde_step_finish(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx,
+                     int64_t B, const float* d_params, const float* d_diag_coeff,
+                     double beta, double alpha, const double* h_eig_w, const double* d_sums,
+                     void* d_workspace, size_t workspace_bytes,
+                     double* d_out_scalars, float* d_grad, void* stream);
+
+/* Single-GPU convenience: epde_step_partial + epde_step_finish with no exchange in between.
+ * Replaces the whole of update_step up to and including loss.backward() (:212-233). */
+int epde_step(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx,
+              int64_t B, const float* d_params, const float* d_diag_coeff,
+              double beta, double alpha, const double* h_eig_w,
+              void* d_workspace, size_t workspace_bytes,
+              double* d_out_scalars, float* d_grad, void* stream);
+
+/*
+ * Forward only: y[B][k] = MyNet.forward on the selected rows (src/network_arch.py:108-117),
+ * used by the stage-end re-normalisation (src/pytorch_eigen_solver.py:120-141) and by
+ * utils/eval_nn_on_*.py.  d_y is fp32 [B][k] row-major.  The workspace only has to be
+ * epde_workspace_bytes(desc, 1) large (it holds the packed weights).
+ */
+int epde_forward(const epde_desc* desc, const float* d_X, const int64_t* d_idx, int64_t B,
+                 const float* d_params, const float* d_diag_coeff, void* d_workspace, size_t workspace_bytes,
+                 float* d_y, void* stream);
+
+/*
+ * Host-side, bit-exact minibatch index stream (src/data_set.py:67 with the cum_weights of
+ * :31): B draws of min(floor(u*K), K-1) from CPython's MT19937, continuing from the
+ * generator state (`h_mt` 624 words + position `*h_pos`, i.e. random.getstate()[1]) and
+ * leaving the advanced state behind, so Python's `random` can resume from it.
+ */
+int epde_minibatch_indices(uint32_t* h_mt, int32_t* h_pos, int64_t K, int64_t B, int64_t* h_idx_out);
+
+/* CPython random.seed(int) -> MT19937 state (init_by_array over the 32-bit words of |seed|);
+ * `h_key` holds the little-endian 32-bit words of the absolute seed. */
+int epde_mt_seed(const uint32_t* h_key, int32_t key_len, uint32_t* h_mt, int32_t* h_pos);
+
+/*
+ * Fused Adam over the flat parameter vector with torch.optim.Adam defaults
+ * (betas 0.9/0.999, eps 1e-8, no weight decay; src/pytorch_eigen_solver.py:234,379),
+ * all in fp32 on the device.  `step` is the 1-based step count after this update.
+ */
+int epde_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                   int64_t n, double lr, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGENPDE_B200_H */
