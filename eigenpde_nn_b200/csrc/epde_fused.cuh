@@ -98,24 +98,48 @@ __global__ void k_pack(const float* __restrict__ params, const float* __restrict
 // pair neighbouring input columns here (natural register pairs of the float4 row loads); the
 // two partial sums are added at the end.  a1 = tanh(z1) as a sample pair.
 template <int H>
+__device__ __forceinline__ void l1_chunk(const float* __restrict__ wrow, const float4 xa, const float4 xb,
+                                         float2 (&s0)[H], float2 (&s1)[H]) {
+#pragma unroll
+  for (int o = 0; o < H; o++) {
+    const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o);
+    s0[o] = ffma2(make_float2(w.x, w.y), make_float2(xa.x, xa.y), s0[o]);
+    s1[o] = ffma2(make_float2(w.x, w.y), make_float2(xb.x, xb.y), s1[o]);
+    s0[o] = ffma2(make_float2(w.z, w.w), make_float2(xa.z, xa.w), s0[o]);
+    s1[o] = ffma2(make_float2(w.z, w.w), make_float2(xb.z, xb.w), s1[o]);
+  }
+}
+
+template <int H>
 __device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1c, const float* __restrict__ sb1,
                                            const float* __restrict__ xr0, const float* __restrict__ xr1, int nj4,
                                            float2 (&a1)[H]) {
   float2 s0[H], s1[H];
   zero2(s0); zero2(s1);
-#pragma unroll 1
-  for (int j4 = 0; j4 < nj4; j4++) {
-    const float4 xa = __ldg(reinterpret_cast<const float4*>(xr0) + j4);
-    const float4 xb = __ldg(reinterpret_cast<const float4*>(xr1) + j4);
-    const float* wrow = sW1c + j4 * (H * 4);
+  // The rows are gathered (random) global reads: keep one group of four float4 per row in
+  // flight ahead of the FFMA2 stream (software pipeline, distance = 4 chunks ~ 640 FMA cycles).
+  constexpr int PF = 4;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ca[PF], cb[PF];
 #pragma unroll
-    for (int o = 0; o < H; o++) {
-      const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o);
-      s0[o] = ffma2(make_float2(w.x, w.y), make_float2(xa.x, xa.y), s0[o]);
-      s1[o] = ffma2(make_float2(w.x, w.y), make_float2(xb.x, xb.y), s1[o]);
-      s0[o] = ffma2(make_float2(w.z, w.w), make_float2(xa.z, xa.w), s0[o]);
-      s1[o] = ffma2(make_float2(w.z, w.w), make_float2(xb.z, xb.w), s1[o]);
+  for (int q = 0; q < PF; q++) {
+    ca[q] = (q < nj4) ? __ldg(reinterpret_cast<const float4*>(xr0) + q) : z4;
+    cb[q] = (q < nj4) ? __ldg(reinterpret_cast<const float4*>(xr1) + q) : z4;
+  }
+#pragma unroll 1
+  for (int j0 = 0; j0 < nj4; j0 += PF) {
+    float4 na[PF], nb[PF];
+#pragma unroll
+    for (int q = 0; q < PF; q++) {
+      const int j = j0 + PF + q;
+      na[q] = (j < nj4) ? __ldg(reinterpret_cast<const float4*>(xr0) + j) : z4;
+      nb[q] = (j < nj4) ? __ldg(reinterpret_cast<const float4*>(xr1) + j) : z4;
     }
+#pragma unroll
+    for (int q = 0; q < PF; q++)
+      if (j0 + q < nj4) l1_chunk<H>(sW1c + (j0 + q) * (H * 4), ca[q], cb[q], s0, s1);
+#pragma unroll
+    for (int q = 0; q < PF; q++) { ca[q] = na[q]; cb[q] = nb[q]; }
   }
 #pragma unroll
   for (int q = 0; q < H / 4; q++) {
@@ -298,7 +322,8 @@ struct RowMap {
   // region 3: rows whose sums are gw4 / gb4
   __host__ __device__ int S4() const { return EB() + 1; }
   __host__ __device__ int YB() const { return S4() + H; }
-  __host__ __device__ int total() const { return YB() + 1; }
+  __host__ __device__ int ONE() const { return YB() + 1; }   // a row of ones (unit scale)
+  __host__ __device__ int total() const { return ONE() + 1; }
 };
 
 struct Coef {                      // written by k_coef, read by k_pass2
@@ -372,7 +397,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
 k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
         int d, int d_pad, int K, const float* __restrict__ pw, const float* __restrict__ ybuf,
         const Coef* __restrict__ coef, float* __restrict__ pg) {
-  static_assert(H % 5 == 0 && H % 4 == 0, "outer-product tiling assumes H multiple of 20");
+  static_assert(H == 20, "outer-product tiling (4x5 tiles, row stride 5) is written for H = 20");
   extern __shared__ float4 smem4[];
   const RowMap<H> R(d);
   const PackLayout<H> L(d_pad);
@@ -386,6 +411,7 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
 
   for (int i = tid; i < L.total(); i += P2_THREADS) sw[i] = pw[(size_t)net * L.total() + i];
   for (int i = tid; i < P2_NG * gn; i += P2_THREADS) accS[i] = 0.f;
+  for (int i = tid; i < P2_TS; i += P2_THREADS) rows[R.ONE() * P2_TS + i] = 1.0f;
   const float ecoef = coef->ecoef[net];
   const float cm = coef->cm[net];
   float cw[8];
@@ -484,23 +510,19 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
     __syncthreads();
 
     // ================= GM1: Gamma, and the g (x) ubar parts of dW2, dW3 ======================
+    // Every work item runs the same code (no divergence inside a warp): only pointers differ.
     {
       constexpr int UPJ = (H / 4) * (H / 5);     // 4x5 tiles of an H x H block
       constexpr int NU = 3 * UPJ;
       constexpr int SG = P2_T / P2_NG;
       for (int wk = tid; wk < NU * P2_NG; wk += P2_THREADS) {
         const int grp = wk / NU, un = wk % NU, job = un / UPJ, t = un % UPJ;
-        const int ot = t % 5, it = t / 5;
-        float* out = accS + grp * gn;
-        if (job == 0)
-          outer_unit<true>(rows + R.G1() * P2_TS, rows + R.G1() * P2_TS, rows + R.EB() * P2_TS, grp * SG, SG,
-                           out + G.Gam(), H, ot, it, H);
-        else if (job == 1)
-          outer_unit<false>(rows + R.G2() * P2_TS, rows + R.U1() * P2_TS, nullptr, grp * SG, SG,
-                            out + G.gW2(), H, ot, it, H);
-        else
-          outer_unit<false>(rows + R.G3() * P2_TS, rows + R.U2() * P2_TS, nullptr, grp * SG, SG,
-                            out + G.gW3(), H, ot, it, H);
+        const int prow = (job == 0) ? R.G1() : (job == 1) ? R.G2() : R.G3();
+        const int qrow = (job == 0) ? R.G1() : (job == 1) ? R.U1() : R.U2();
+        const int srow = (job == 0) ? R.EB() : R.ONE();
+        const int oo = (job == 0) ? G.Gam() : (job == 1) ? G.gW2() : G.gW3();
+        outer_unit<true>(rows + prow * P2_TS, rows + qrow * P2_TS, rows + srow * P2_TS, grp * SG, SG,
+                         accS + grp * gn + oo, H, t % 5, t / 5, H);
       }
     }
     __syncthreads();
@@ -545,29 +567,25 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
       const int njt = R.xr / 5;
       const int nu1 = 5 * njt;                   // (H/4) * njt units for dW1
       const int NU = nu1 + 2 * UPJ;
-      const int nrows = 4 * H + 1;
-      for (int wk = tid; wk < NU + nrows; wk += P2_THREADS) {
-        float* out = accS;                       // group 0 accumulates GM2
-        if (wk < nu1) {
-          outer_unit<false>(rows + R.Z1() * P2_TS, rows + R.XT() * P2_TS, nullptr, 0, P2_T,
-                            out + G.gW1(), d_pad, wk % 5, wk / 5, d);
-        } else if (wk < nu1 + UPJ) {
-          const int t = wk - nu1;
-          outer_unit<false>(rows + R.Z2() * P2_TS, rows + R.A1() * P2_TS, nullptr, 0, P2_T,
-                            out + G.gW2(), H, t % 5, t / 5, H);
-        } else if (wk < NU) {
-          const int t = wk - nu1 - UPJ;
-          outer_unit<false>(rows + R.Z3() * P2_TS, rows + R.A2() * P2_TS, nullptr, 0, P2_T,
-                            out + G.gW3(), H, t % 5, t / 5, H);
-        } else {
-          const int r = wk - NU;
-          float* o1 = accS + gn;                 // group 1 copy: no overlap with GM2 unit outputs
-          if (r < H) row_sum(rows + (R.Z1() + r) * P2_TS, o1 + G.gb1() + r);
-          else if (r < 2 * H) row_sum(rows + (R.Z2() + r - H) * P2_TS, o1 + G.gb2() + r - H);
-          else if (r < 3 * H) row_sum(rows + (R.Z3() + r - 2 * H) * P2_TS, o1 + G.gb3() + r - 2 * H);
-          else if (r < 4 * H) row_sum(rows + (R.S4() + r - 3 * H) * P2_TS, o1 + G.gw4() + r - 3 * H);
-          else row_sum(rows + R.YB() * P2_TS, o1 + G.gb4());
-        }
+      for (int wk = tid; wk < NU; wk += P2_THREADS) {
+        const int job = (wk < nu1) ? 0 : (wk < nu1 + UPJ) ? 1 : 2;
+        const int t = (job == 0) ? wk : (job == 1) ? wk - nu1 : wk - nu1 - UPJ;
+        const int prow = (job == 0) ? R.Z1() : (job == 1) ? R.Z2() : R.Z3();
+        const int qrow = (job == 0) ? R.XT() : (job == 1) ? R.A1() : R.A2();
+        const int oo = (job == 0) ? G.gW1() : (job == 1) ? G.gW2() : G.gW3();
+        const int ld = (job == 0) ? d_pad : H, imax = (job == 0) ? d : H;
+        outer_unit<false>(rows + prow * P2_TS, rows + qrow * P2_TS, nullptr, 0, P2_T, accS + oo, ld, t % 5, t / 5,
+                          imax);
+      }
+      const int nrows = 4 * H + 1;               // bias / w4 row sums on the threads without a unit
+      const int first = (NU < P2_THREADS) ? NU : 0, nfree = P2_THREADS - first;
+      for (int r = tid - first; r >= 0 && r < nrows; r += nfree) {
+        const int q = r / H, o = r % H;
+        const int srow = (q == 0) ? R.Z1() + o : (q == 1) ? R.Z2() + o : (q == 2) ? R.Z3() + o
+                       : (q == 3) ? R.S4() + o : R.YB();
+        const int oo = (q == 0) ? G.gb1() + o : (q == 1) ? G.gb2() + o : (q == 2) ? G.gb3() + o
+                     : (q == 3) ? G.gw4() + o : G.gb4();
+        row_sum(rows + srow * P2_TS, accS + oo);
       }
     }
     __syncthreads();
