@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "../../include/eigenpde_b200.h"
+#include "epde_coef.cuh"
 #include "epde_fused.cuh"
 #include "epde_generic.cuh"
 
@@ -80,68 +81,6 @@ __global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, d
   double v = 0.0;
   for (int b = 0; b < nb; b++) v += part[(size_t)b * ns + s];
   sums[s] = v;
-}
-
-struct EigW { double v[EPDE_MAX_K]; };
-
-// Everything that depends only on the batch-global sums: eig_vals, cvec, losses
-// (src/pytorch_eigen_solver.py:215-229, 177-189) and the per-sample seed coefficients of the
-// reverse pass (SURVEY.md 8(a) closed form).  One thread; k <= 8.
-__global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
-                       double* __restrict__ out, Coef* __restrict__ coef) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double W = sums[0];
-  const double* S1 = sums + 1;
-  const double* E = sums + 1 + k;
-  const double* S2 = sums + 1 + 2 * k;
-  double m[EPDE_MAX_K], var[EPDE_MAX_K], Rq[EPDE_MAX_K], lam[EPDE_MAX_K], wt[EPDE_MAX_K];
-  double cov[EPDE_MAX_K][EPDE_MAX_K];
-  int cvec[EPDE_MAX_K];
-  for (int i = 0; i < k; i++) m[i] = S1[i] / W;
-  int t = 0;
-  for (int i = 0; i < k; i++)
-    for (int j = 0; j <= i; j++) { cov[i][j] = cov[j][i] = S2[t] / W - m[i] * m[j]; t++; }
-  for (int i = 0; i < k; i++) {
-    var[i] = cov[i][i];
-    Rq[i] = E[i] / (W * beta);
-    lam[i] = Rq[i] / var[i];
-    cvec[i] = i;
-  }
-  if (sort) {   // ascending, stable insertion sort (np.argsort order for distinct values)
-    for (int i = 1; i < k; i++) {
-      const int c = cvec[i]; int j = i - 1;
-      while (j >= 0 && lam[cvec[j]] > lam[c]) { cvec[j + 1] = cvec[j]; j--; }
-      cvec[j + 1] = c;
-    }
-  }
-  for (int p = 0; p < k; p++) wt[cvec[p]] = eigw.v[p];
-  double nonpen = 0.0, pen = 0.0;
-  for (int i = 0; i < k; i++) { nonpen += wt[i] * lam[i]; pen += (var[i] - 1.0) * (var[i] - 1.0); }
-  for (int i = 0; i < k; i++)
-    for (int j = i + 1; j < k; j++) pen += cov[i][j] * cov[i][j];
-  out[EPDE_OUT_LOSS] = nonpen + alpha * pen;
-  out[EPDE_OUT_NONPEN] = nonpen;
-  out[EPDE_OUT_PENALTY] = pen;
-  out[EPDE_OUT_TOTW] = W;
-  for (int p = 0; p < k; p++) {
-    out[EPDE_OUT_EIG(k) + p] = lam[cvec[p]];
-    out[EPDE_OUT_CVEC(k) + p] = (double)cvec[p];
-    out[EPDE_OUT_MEAN(k) + p] = m[p];
-    out[EPDE_OUT_VAR(k) + p] = var[p];
-  }
-  if (coef) {
-    for (int i = 0; i < k; i++) {
-      coef->ecoef[i] = (float)(wt[i] / (W * beta * var[i]));
-      double cmi = 0.0;
-      for (int j = 0; j < k; j++) {
-        const double c = (i == j) ? 2.0 * (-wt[i] * Rq[i] / (var[i] * var[i]) + 2.0 * alpha * (var[i] - 1.0))
-                                  : 2.0 * alpha * cov[i][j];
-        coef->Cw[i][j] = (float)(c / W);
-        cmi += c / W * m[j];
-      }
-      coef->cm[i] = (float)cmi;
-    }
-  }
 }
 
 template <int K>
@@ -275,8 +214,7 @@ int epde_step_finish(const epde_desc* D, const float* X, const float* w, const i
   for (int i = 0; i < D->k; i++) ew.v[i] = h_eig_w[i];
   cudaStream_t st = (cudaStream_t)stream;
   if (fused_ok(D)) return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, st);
-  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, nullptr);
-  return generic_finish(D, X, w, idx, B, params, diag, beta, alpha, ew.v, sums, ws, out, grad, st);
+  return generic_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, st);
 }
 
 int epde_step(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
@@ -299,7 +237,7 @@ int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t
   size_t need; rc = epde_workspace_bytes(D, 1, &need); if (rc) return rc;
   if (ws_bytes < need) return EPDE_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!fused_ok(D)) return generic_forward(D, X, idx, B, params, ws, y, st);
+  if (!fused_ok(D)) return generic_forward(D, X, idx, B, params, ws, ws_bytes, y, st);
   FusedWs W = fused_ws(D, 1, ws);
   int nsm; rc = sm_count(&nsm); if (rc) return rc;
   k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);

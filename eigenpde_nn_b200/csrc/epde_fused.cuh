@@ -10,6 +10,7 @@
 // shared memory (one LDS.128 per four FFMA2).
 #pragma once
 #include "epde_common.cuh"
+#include "epde_coef.cuh"
 
 namespace epde {
 
@@ -324,12 +325,6 @@ struct RowMap {
   __host__ __device__ int YB() const { return S4() + H; }
   __host__ __device__ int ONE() const { return YB() + 1; }   // a row of ones (unit scale)
   __host__ __device__ int total() const { return ONE() + 1; }
-};
-
-struct Coef {                      // written by k_coef, read by k_pass2
-  float ecoef[8];                  // ebar_{n,i} = w_n * ecoef[i]
-  float cm[8];                     // ybar_{n,i} = w_n * (sum_j Cw[i][j] y_{n,j} - cm[i])
-  float Cw[8][8];
 };
 
 template <int H>

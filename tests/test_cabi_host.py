@@ -1,0 +1,131 @@
+"""CPU: the C-ABI library loads, exports what include/eigenpde_b200.h declares, and its host-side
+entry points (descriptor checks, sizes, MT19937 minibatch stream) behave.  No compute calls."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from oracle import minibatch
+
+
+@pytest.fixture(scope="module")
+def L():
+    from eigenpde_nn_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_exports_match_header(L):
+    from eigenpde_nn_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "eigenpde_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(epde_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.epde_abi_version() == 1
+    assert L.epde_error_string(0) == b"ok"
+    assert b"workspace" in L.epde_error_string(-4)
+
+
+def test_param_count_and_sums(L):
+    from eigenpde_nn_b200 import _lib
+    for arch, k, want in [([50, 20, 20, 20, 1], 3, 5643), ([2, 20, 20, 20, 1], 2, 1842), ([30, 20, 20, 20, 1], 2, 2962),
+                          ([50, 20, 20, 20, 1], 6, 11286), ([50, 256, 256, 256, 256, 1], 4, 842756)]:
+        D = _lib.make_desc(arch, k, "Tanh", (arch[0] + 3) // 4 * 4)
+        n = C.c_int64()
+        assert L.epde_param_count(C.byref(D), C.byref(n)) == 0 and n.value == want
+        ns = C.c_int32()
+        assert L.epde_num_sums(C.byref(D), C.byref(ns)) == 0 and ns.value == 1 + 2 * k + k * (k + 1) // 2
+    D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
+    assert L.epde_has_fused_path(C.byref(D)) == 1
+    D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Softplus", 52)
+    assert L.epde_has_fused_path(C.byref(D)) == 0
+    D = _lib.make_desc([50, 256, 256, 256, 256, 1], 4, "Tanh", 52)
+    assert L.epde_has_fused_path(C.byref(D)) == 0
+
+
+def test_descriptor_validation(L):
+    from eigenpde_nn_b200 import _lib
+    n = C.c_int64()
+    D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 50)       # d_pad not a multiple of 4
+    assert L.epde_param_count(C.byref(D), C.byref(n)) == -5
+    D = _lib.make_desc([50, 20, 20, 20, 2], 3, "Tanh", 52)       # output width must be 1
+    assert L.epde_param_count(C.byref(D), C.byref(n)) == -2
+    D = _lib.make_desc([50, 20, 20, 20, 1], 9, "Tanh", 52)       # k > EPDE_MAX_K
+    assert L.epde_param_count(C.byref(D), C.byref(n)) == -2
+    D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
+    assert L.epde_param_count(None, C.byref(n)) == -1
+    sz = C.c_size_t()
+    assert L.epde_workspace_bytes(C.byref(D), 0, C.byref(sz)) == -6
+    assert L.epde_workspace_bytes(C.byref(D), 5000, C.byref(sz)) == 0 and sz.value > 5000 * 3 * 4
+    # compute entry points refuse NULL buffers before touching the device
+    assert L.epde_step(C.byref(D), None, None, None, 10, None, None, 1.0, 20.0, None, None, 0, None, None, None) == -1
+    # unknown activation names fall back to CELU like network_arch.py:27-32
+    assert _lib.make_desc([8, 12, 12, 1], 2, "NoSuchAct", 8).act_id == _lib.ACT_IDS["CELU"]
+
+
+def _seed_state(L, seed):
+    key = []
+    s = abs(seed)
+    while True:
+        key.append(s & 0xFFFFFFFF); s >>= 32
+        if s == 0:
+            break
+    karr = (C.c_uint32 * len(key))(*key)
+    mt = (C.c_uint32 * 624)()
+    pos = C.c_int32()
+    assert L.epde_mt_seed(karr, len(key), mt, C.byref(pos)) == 0
+    return mt, pos
+
+
+def test_mt_seed_matches_cpython(L):
+    for seed in [0, 1, 3214, 3905 + 1792443474, 2 ** 40 + 17, 2 ** 70 + 12345]:
+        mt, pos = _seed_state(L, seed)
+        random.seed(seed)
+        st = random.getstate()[1]
+        assert list(mt) == list(st[:624]) and pos.value == st[624] == 624
+        assert np.array_equal(np.array(list(mt), dtype=np.uint32), minibatch.seed_state(seed))
+
+
+def test_minibatch_stream_bit_exact_vs_reference_fixture(L):
+    z = np.load(os.path.join(GOLDEN, "index_streams.npz"))
+    n = 0
+    while f"s{n}_meta" in z:
+        seed, K, B, reps = (int(v) for v in z[f"s{n}_meta"])
+        mt, pos = _seed_state(L, seed)
+        for r in range(reps):
+            out = np.empty(B, dtype=np.int64)
+            assert L.epde_minibatch_indices(mt, C.byref(pos), K, B, out.ctypes.data_as(C.c_void_p)) == 0
+            assert np.array_equal(out, z[f"s{n}_idx"][r]), (seed, K, B, r)
+        n += 1
+
+
+def test_minibatch_interleaves_with_python_random(L):
+    """random.getstate() -> native draw -> random.setstate(): Python's stream continues unbroken."""
+    K, B = 123457, 1001
+    random.seed(99)
+    random.random()                                  # odd position inside the 624 block
+    want = random.choices(range(K), cum_weights=np.arange(1, K + 1), k=B)
+    after = random.random()
+    random.seed(99)
+    random.random()
+    ver, st, gauss = random.getstate()
+    mt = (C.c_uint32 * 624)(*st[:624]); pos = C.c_int32(st[624])
+    out = np.empty(B, dtype=np.int64)
+    assert L.epde_minibatch_indices(mt, C.byref(pos), K, B, out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(out, np.asarray(want))
+    random.setstate((ver, tuple(mt) + (pos.value,), gauss))
+    assert random.random() == after
+
+
+def test_minibatch_edge_cases(L):
+    mt, pos = _seed_state(L, 5)
+    out = np.empty(4, dtype=np.int64)
+    assert L.epde_minibatch_indices(mt, C.byref(pos), 1, 4, out.ctypes.data_as(C.c_void_p)) == 0
+    assert (out == 0).all()                          # K = 1: every draw is row 0
+    assert L.epde_minibatch_indices(mt, C.byref(pos), 10, 0, out.ctypes.data_as(C.c_void_p)) == 0   # empty batch
+    assert L.epde_minibatch_indices(mt, C.byref(pos), 0, 4, out.ctypes.data_as(C.c_void_p)) == -6
