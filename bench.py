@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""Benchmark of the fused loss+gradient step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+Workload (config.workload = "ex1_50d_k3"): 50-D, arch 50-20-20-20-1, Tanh, k = 3, beta = 1,
+alpha = 20, eig_w = (1.0, 0.8, 0.6) -- examples/test-ex1-50d/params.cfg -- on a synthetic
+trajectory of 2^22 states (ring in (x0,x1), N(0,0.1) elsewhere), lognormal weights.
+One step = one pass of the hot path (src/pytorch_eigen_solver.py:212-233) over one minibatch of
+B = 2^20 samples per GPU (weak scaling: the global batch is N * 2^20, sharded by contiguous slices).
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with the index batch already on the device;
+`e2e` = the same step through the host-facing API with host (pinned) index/parameter buffers and
+the gradient + scalars read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, KNETS, ARCH = 50, 3, [50, 20, 20, 20, 1]
+EIG_W, BETA, ALPHA = [1.0, 0.8, 0.6], 1.0, 20.0
+K_DATA = 1 << 22
+M_MACS = 50 * 20 + 20 * 20 + 20 * 20 + 20
+FLOP_ALG = 2 * KNETS * (6 * M_MACS - 50 * 20)            # 59 520 per sample
+FLOP_ALG_P1 = 2 * KNETS * 2 * M_MACS                     # forward + input-Jacobian share (phase 1)
+BYTES_ALG = 4 * D + 4 + 8                                # x row + weight + int64 index
+FFMA_PEAK_TFLOPS = 72.99     # measured on this pool's B200: profiles/ffma_peak_r1.jsonl (nominal 74.4)
+
+
+def synth_data(device, seed, K=K_DATA):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    X = torch.zeros((K, 52), dtype=torch.float32, device=device)
+    X[:, :D] = (0.1 ** 0.5) * torch.randn((K, D), generator=g, device=device)
+    th = 2 * torch.pi * torch.rand(K, generator=g, device=device)
+    r = 1.0 + 0.3 * torch.randn(K, generator=g, device=device)
+    X[:, 0] = r * torch.cos(th)
+    X[:, 1] = r * torch.sin(th)
+    w = torch.exp(0.5 * torch.randn(K, generator=g, device=device))
+    w /= w.mean()
+    return X, w
+
+
+def init_params(seed):
+    """N(0, 0.5) for every weight and bias, as network_arch.py:37-39."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n = KNETS * sum(ARCH[l + 1] * ARCH[l] + ARCH[l + 1] for l in range(len(ARCH) - 1))
+    return 0.5 * torch.randn(n, generator=g)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_lo, self.t_hi = None, None
+
+    def mark_start(self):
+        self.t_lo = time.time()
+
+    def mark_stop(self):
+        self.t_hi = time.time()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        lo = self.t_lo or 0.0
+        hi = self.t_hi or time.time()
+        rows = [r for (t, r) in self.rows if lo <= t <= hi + 0.05 and len(r) >= 9]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            if len(r) >= 9:
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        smax = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(B, steps, warmup, seed=0):
+    """samples/s of the oracle port (oracle/ref_port.py, torch fp64 autograd on the host cores):
+    (a) update_step as shipped (minibatch + loss + backward + Adam), (b) loss + gradient only."""
+    import numpy as np
+    import torch
+    from oracle import ref_port
+    rng = np.random.default_rng(seed)
+    Kd = max(4 * B, 100000)
+    X = np.sqrt(0.1) * rng.standard_normal((Kd, D))
+    th = rng.uniform(0, 2 * np.pi, Kd)
+    r = 1.0 + 0.3 * rng.standard_normal(Kd)
+    X[:, 0], X[:, 1] = r * np.cos(th), r * np.sin(th)
+    w = np.exp(0.5 * rng.standard_normal(Kd)); w /= w.mean()
+    torch.manual_seed(seed)
+    model = ref_port.PortNet(ARCH, "Tanh", KNETS).double()
+    solver = ref_port.PortSolver(model, X, w, np.ones(D), BETA, EIG_W)
+    import random
+    random.seed(seed)
+    t_full, t_lg = [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, xb, wb = solver.minibatch(B)
+        t1 = time.perf_counter()
+        solver.loss_grad(xb, wb, ALPHA)
+        t2 = time.perf_counter()
+        solver.optimizer.step()
+        t3 = time.perf_counter()
+        if i >= warmup:
+            t_full.append(t3 - t0); t_lg.append(t2 - t1)
+    return B / statistics.median(t_full), B / statistics.median(t_lg), torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path, timed on the host cores.
+    /root/reference is Python and cannot travel to the GPU box; the oracle port restates it op by op
+    (pinned against the reference's own outputs in tests/golden)."""
+    if rank != 0:
+        return
+    B = 20000                      # the reference's own stage-2 batch size (params.cfg:39)
+    t0 = time.perf_counter()
+    full, lg, cores = cpu_port_rate(B, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "samples/s, fused loss+grad step, 50-D k=3", "value": lg,
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * B / lg, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ex1_50d_k3", "d": D, "k": KNETS, "arch": ARCH, "batch_per_step": B},
+            "cpu_baseline": {"value": lg, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "B=20000 per step, %d timed steps, loss+grad only (update_step as shipped incl. "
+                                       "minibatch+Adam: %.0f samples/s)" % (args.steps, full)},
+            "e2e": {"value": lg, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    from eigenpde_nn_b200.engine import StepEngine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    W = max(args.warmup, 3)
+    B = args.batch
+    X, w = synth_data(dev, seed=1234)                       # replicated data set (872 MB fp32)
+    eng = StepEngine(X, w, ARCH, KNETS, "Tanh", np.ones(D), BETA, EIG_W, device=dev, process_group=pg)
+    assert eng.fused
+    params_h = init_params(7).pin_memory()
+    params = params_h.to(dev)
+    nbatch = 4                                              # distinct index batches, cycled
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    idx_dev = [torch.randint(0, K_DATA, (B,), generator=g, device=dev, dtype=torch.int64) for _ in range(nbatch)]
+    idx_pin = [t.cpu().pin_memory() for t in idx_dev]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(W):
+        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA)
+    barrier()
+    sampler.mark_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    out_h = eng.out.cpu().numpy()
+
+    # ---- per-phase timing of the dominant kernel (k_pass2 inside epde_step_finish) ----------
+    import ctypes as C
+    from eigenpde_nn_b200 import _lib
+    ws = eng._workspace(B)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    eigw = (C.c_double * KNETS)(*EIG_W)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_p1 = t_p2 = 0.0
+    nphase = min(args.steps, 10)
+    for i in range(nphase):
+        ib = idx_dev[i % nbatch]
+        a = (C.byref(eng.desc), X.data_ptr(), w.data_ptr(), ib.data_ptr(), B, params.data_ptr(), eng.diag.data_ptr())
+        evs[0].record()
+        _lib.check(eng.lib.epde_step_partial(*a, ws.data_ptr(), ws.numel(), eng.sums.data_ptr(), st), "partial")
+        evs[1].record()
+        _lib.check(eng.lib.epde_step_finish(*a, BETA, ALPHA, eigw, eng.sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            eng.out.data_ptr(), eng.grad.data_ptr(), st), "finish")
+        evs[2].record()
+        torch.cuda.synchronize()
+        t_p1 += evs[0].elapsed_time(evs[1]); t_p2 += evs[1].elapsed_time(evs[2])
+    t_p1 /= nphase; t_p2 /= nphase
+
+    # ---- end to end through the host-facing API --------------------------------------------
+    out_pin = torch.empty(eng.out.numel(), dtype=torch.float64).pin_memory()
+    grad_pin = torch.empty(eng.n_params, dtype=torch.float32).pin_memory()
+    idx_stage = torch.empty(B, dtype=torch.int64, device=dev)
+    par_stage = torch.empty_like(params)
+
+    def e2e_step(i):
+        idx_stage.copy_(idx_pin[i % nbatch], non_blocking=True)       # H2D: this step's minibatch indices
+        par_stage.copy_(params_h, non_blocking=True)                   # H2D: current parameters
+        o, gr = eng.step_device(idx_stage, B, par_stage, ALPHA)
+        out_pin.copy_(o, non_blocking=True)                            # D2H: loss / eigenvalues / penalty
+        grad_pin.copy_(gr, non_blocking=True)                          # D2H: gradient for the host optimiser
+        torch.cuda.current_stream().synchronize()                      # update_step returns host values (:236)
+        return float(out_pin[0])
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # clocks are sampled (20 ms period) over the whole measured span: device-timed steps, per-phase
+    # timing and the end-to-end steps -- all of them back-to-back launches of the same kernels
+    sampler.mark_stop()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_s, t_p1, t_p2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, t_p1, t_p2 = (float(v) for v in t.cpu())
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    total = world * B * args.steps
+    value = total / (ms * 1e-3)
+    ach2 = (FLOP_ALG - FLOP_ALG_P1) * B / (t_p2 * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "pass2_dram_bytes.json")
+    if os.path.exists(prof):
+        pj = json.load(open(prof))
+        traffic = pj.get("dram_bytes_per_launch") if pj.get("batch") == B else None
+    line = {
+        "metric": "samples/s, fused loss+grad step, 50-D k=3", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ex1_50d_k3", "d": D, "k": KNETS, "arch": ARCH, "activation": "Tanh",
+                   "batch_per_gpu": B, "global_batch": world * B, "dataset_rows": K_DATA,
+                   "parallelism": "dp%d (batch sharded, 2 NCCL allreduces/step)" % world if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: 872 MB data set gathered by fresh random indices each step"},
+        "loss": float(out_h[0]), "eig_vals": [float(v) for v in out_h[4:4 + KNETS]],
+        "roofline": {"bound": "fp32_ffma", "kernel": "k_pass2 (epde_step_finish)", "achieved": ach2,
+                     "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach2 / FFMA_PEAK_TFLOPS,
+                     "traffic": traffic, "ms_per_launch": t_p2,
+                     "peak_source": "measured FFMA peak, tools/microbench/ffma_peak.cu (MEASURED_PEAKS.json has no "
+                                    "FP32 figure; nominal 74.4 TFLOP/s)",
+                     "step": {"achieved": FLOP_ALG * B / ((t_p1 + t_p2) * 1e-3) / 1e12,
+                              "frac": FLOP_ALG * B / ((t_p1 + t_p2) * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS,
+                              "ms_phase1": t_p1, "ms_phase2": t_p2, "flop_per_sample": FLOP_ALG},
+                     "hbm": {"achieved_gbs": BYTES_ALG * B / ((t_p1 + t_p2) * 1e-3) / 1e9, "peak_gbs": 6544.3}},
+        "e2e": {"value": total / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 8 * B + 4 * eng.n_params,
+                "d2h_bytes_per_step": 8 * eng.out.numel() + 4 * eng.n_params},
+        "gpu_launches": 6 * args.steps, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        full, lg, cores = cpu_port_rate(20000, 12, 3)
+        line["cpu_baseline"] = {"value": lg, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": "oracle/ref_port.py (torch fp64 autograd), B=20000, 12 timed steps, loss+grad "
+                                          "only; update_step as shipped (minibatch+Adam): %.0f samples/s" % full}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,11 +56,17 @@ class StepEngine:
         self.n_sums = ns.value
         self.fused = self.lib.epde_has_fused_path(C.byref(self.desc)) == 1
         with torch.cuda.device(self.device):
-            Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32)
-            self.K = Xt.shape[0]
-            self.X = torch.zeros((self.K, self.d_pad), dtype=torch.float32, device=self.device)
-            self.X[:, : self.d] = Xt.to(self.device)
-            self.w = torch.as_tensor(np.asarray(weights), dtype=torch.float32).to(self.device).contiguous()
+            if isinstance(X, torch.Tensor) and X.is_cuda:
+                # already a device mirror: [K, d_pad] fp32 with zero padding columns
+                assert X.dtype == torch.float32 and X.shape[1] == self.d_pad and X.is_contiguous()
+                self.X, self.K = X, X.shape[0]
+                self.w = weights.to(self.device, torch.float32).contiguous()
+            else:
+                Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+                self.K = Xt.shape[0]
+                self.X = torch.zeros((self.K, self.d_pad), dtype=torch.float32, device=self.device)
+                self.X[:, : self.d] = Xt.to(self.device)
+                self.w = torch.as_tensor(np.asarray(weights), dtype=torch.float32).to(self.device).contiguous()
             self.diag = torch.as_tensor(np.asarray(diag_coeff), dtype=torch.float32).to(self.device).contiguous()
             self.sums = torch.zeros(self.n_sums, dtype=torch.float64, device=self.device)
             self.out = torch.zeros(4 + 4 * self.k, dtype=torch.float64, device=self.device)

@@ -173,6 +173,41 @@ def index_streams():
     return out
 
 
+def dropin_run(pes):
+    """A short end-to-end training run of the UNMODIFIED reference (eigen_solver.run) on a small
+    data file: its log.txt lines and final checkpoints pin the drop-in facade."""
+    import torch
+    rng = np.random.default_rng(99)
+    case = dict(K=3000, d=50, data="ring50", weights="lognormal")
+    X, w = synth_data(case, rng)
+    X, w = np.round(X, 10), np.round(w, 10)          # what "%.10f" text round-trips to
+    seed = 4321
+    P = types.SimpleNamespace(
+        k=3, eig_w=[1.0, 0.8, 0.6, 0.3, 0.2, 0.1], md_data_flag=False, md_beta=1.0, beta=1.0, diffusion_coeff=0.0,
+        stage_list=[0, 6, 10], batch_size_list=[500, 800], sort_eigvals_in_training=True,
+        learning_rate_list=[5e-3, 2e-3], alpha_list=[20.0, 10.0], inner_arch_size_list=[20, 20, 20],
+        activation_name="Tanh", train_max_step=10, load_init_model=False, init_model_name="x.pt",
+        print_every_step=1, data_filename_prefix="states", eig_file_name_prefix="eig", log_filename="log.txt")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as wd:
+        os.makedirs(os.path.join(wd, "data"))
+        with open(os.path.join(wd, "data", "states.txt"), "w") as f:
+            f.write("%d %d\n" % X.shape)
+            np.savetxt(f, np.concatenate([X, w[:, None]], axis=1), fmt="%.10f")
+        os.chdir(wd)
+        try:
+            solver = pes.eigen_solver(P, seed)
+            solver.run()
+            log = open(os.path.join(wd, "data", "log.txt")).read()
+            ck = {}
+            for name in ["eig", "eig_averaged", "eig_stage1", "eig_stage2_averaged"]:
+                m = torch.load(os.path.join(wd, "data", name + ".pt"), weights_only=False)
+                ck[name] = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).numpy()
+        finally:
+            os.chdir(cwd)
+    return dict(X=X, w=w, seed=np.int64(seed), log=np.str_(log), **{"ck_" + k: v for k, v in ck.items()})
+
+
 def main():
     pes, na, ds = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -184,6 +219,8 @@ def main():
                                                          out["cvec"], os.path.getsize(path) / 1024))
     np.savez_compressed(os.path.join(OUT, "index_streams.npz"), **index_streams())
     print("index streams written")
+    np.savez_compressed(os.path.join(OUT, "dropin_run.npz"), **dropin_run(pes))
+    print("drop-in run written")
 
 
 if __name__ == "__main__":
