@@ -107,14 +107,18 @@ class StepEngine:
                                           _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), st),
                        "epde_step")
         else:
-            import torch.distributed as dist
-            _lib.check(self.lib.epde_step_partial(*args, _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.sums), st),
-                       "epde_step_partial")
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.pg)
-            _lib.check(self.lib.epde_step_finish(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
-                                                 _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out),
-                                                 _ptr(self.grad), st), "epde_step_finish")
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            from .parallel import two_phase_step
+
+            def partial():
+                _lib.check(self.lib.epde_step_partial(*args, _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.sums), st),
+                           "epde_step_partial")
+
+            def finish():
+                _lib.check(self.lib.epde_step_finish(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                                     _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()),
+                                                     _ptr(self.out), _ptr(self.grad), st), "epde_step_finish")
+
+            two_phase_step(partial, finish, self.sums, self.grad, self.pg)
         return self.out, self.grad
 
     def step(self, idx, params_dev, alpha):

@@ -161,11 +161,15 @@ def coefficients(W, S1, S2, E, beta, alpha, eig_w, sort=True):
                 C=C, ebar_coef=ebar_coef, lam=lam, W=W)
 
 
-def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=True):
+def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=True, global_sums=None,
+         sums_only=False):
     """Loss, eigenvalue estimates and parameter gradients for one batch.
 
     x [B,d] fp64 (already gathered), w [B] fp64.
     Returns dict; grads has the same nesting as params.
+    global_sums=(W,S1,S2,E): use these batch-global sums instead of the local ones (the samples
+    given are then one shard of the batch and `grads` is that shard's additive share).
+    sums_only: stop after the local sums (phase 1 of a sharded step).
     """
     act = ACTIVATIONS[activation]
     x = np.asarray(x, dtype=np.float64)
@@ -181,6 +185,10 @@ def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=T
     y = np.stack(ys, axis=1)
     e = np.stack([(c[None, :] * u[0] ** 2).sum(axis=1) for u in us], axis=1)
     W, S1, S2, E = batch_sums(y, e, w)
+    if sums_only:
+        return dict(sums=dict(W=W, S1=S1, S2=S2, E=E), y=y, e=e)
+    if global_sums is not None:
+        W, S1, S2, E = global_sums
     co = coefficients(W, S1, S2, E, beta, alpha, eig_w, sort)
     ybar = (w / W)[:, None] * ((y - co["mean"][None, :]) @ co["C"])  # C symmetric
     grads = []
