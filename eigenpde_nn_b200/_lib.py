@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeigenpde_b200.so")
+LIB_PATH = os.environ.get("EPDE_LIB", os.path.join(HERE, "libeigenpde_b200.so"))   # EPDE_LIB: developer override
 
 EPDE_MAX_LAYERS = 8
 EPDE_MAX_K = 8

@@ -16,6 +16,7 @@ namespace {
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
 constexpr int kFusedH = 20;
 constexpr size_t kSumsTail = 2048;
+constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -50,7 +51,7 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 
 // ---- workspace ------------------------------------------------------------------------------
 struct FusedWs {
-  float* pw; float* ybuf; double* part; Coef* coef; float* pg; size_t total;
+  float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; size_t total;
 };
 FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   char* p = (char*)base; size_t off = 0; FusedWs W;
@@ -60,6 +61,9 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.part = (double*)take((size_t)kMaxCtas * num_sums(D->k) * 8);
   W.coef = (Coef*)take(sizeof(Coef));
   W.pg = (float*)take((size_t)kMaxCtas * GradLayout<kFusedH>(D->d_pad).total() * 4);
+  const size_t ntl = (size_t)((B + GT - 1) / GT);
+  W.xt = (float*)take(ntl * D->d_pad * GT * 4);
+  W.wt = (float*)take(ntl * GT * 4);
   W.total = off;
   return W;
 }
@@ -84,11 +88,21 @@ __global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, d
 }
 
 template <int K>
-cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* X, const float* w, const int64_t* idx,
-                         int64_t B, int d_pad, const float* pw, float* ybuf, double* part) {
+cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt, const float* wt, int64_t B, int d,
+                         int d_pad, const float* pw, float* ybuf, double* part) {
   cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(X, w, idx, B, d_pad, pw, ybuf, part);
+  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part);
+  return cudaGetLastError();
+}
+
+// gather + transpose the minibatch rows into the tile-major copy (workspace xt / wt)
+cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                          float* xt, float* wt, cudaStream_t st) {
+  const size_t smem = (size_t)GT * (D->d_pad + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_gather<0><<<(unsigned)((B + GT - 1) / GT), 256, smem, st>>>(X, w, idx, B, D->d_pad, xt, wt);
   return cudaGetLastError();
 }
 
@@ -97,19 +111,24 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
+  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st);
+  if (e != cudaSuccess) return (int)e;
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
   const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
-  cudaError_t e;
+#ifdef EPDE_DEV_ONLY_K3
+  e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part);
+#else
   switch (D->k) {
-    case 1: e = launch_pass1<1>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 2: e = launch_pass1<2>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 3: e = launch_pass1<3>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 4: e = launch_pass1<4>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 5: e = launch_pass1<5>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
-    default: e = launch_pass1<6>(grid, smem, st, X, w, idx, B, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
   }
+#endif
   if (e != cudaSuccess) return (int)e;
   k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums);
   return (int)cudaGetLastError();
@@ -127,7 +146,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   const size_t smem = pass2_smem_bytes<kFusedH>(D->d, D->d_pad);
   cudaError_t e = cudaFuncSetAttribute(k_pass2<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(X, w, idx, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
+  k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
                                                               W.coef, W.pg);
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
@@ -149,6 +168,15 @@ int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, 
 }  // namespace
 
 extern "C" {
+
+#ifdef EPDE_PHASE_TIMING
+// profiling aid (only in -DEPDE_PHASE_TIMING builds): cycles thread 0 of each CTA spent per phase
+int epde_debug_phase_cycles(unsigned long long* h8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(h8, g_phase_cycles, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && reset) { unsigned long long z[8] = {0}; e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+  return (int)e;
+}
+#endif
 
 int epde_abi_version(void) { return EPDE_ABI_VERSION; }
 
@@ -234,20 +262,28 @@ int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t
   if (!X || !params || !y || !ws || !diag) return EPDE_ERR_NULL;
   if (B < 1) return EPDE_ERR_ARG;
   if (((uintptr_t)X & 15) || ((uintptr_t)ws & 255)) return EPDE_ERR_ALIGN;
-  size_t need; rc = epde_workspace_bytes(D, 1, &need); if (rc) return rc;
+  const int64_t slab = B < kFwdSlab ? B : kFwdSlab;
+  size_t need; rc = epde_workspace_bytes(D, slab, &need); if (rc) return rc;
   if (ws_bytes < need) return EPDE_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   if (!fused_ok(D)) return generic_forward(D, X, idx, B, params, ws, ws_bytes, y, st);
-  FusedWs W = fused_ws(D, 1, ws);
+  // forward in slabs of at most kFwdSlab samples so the workspace stays small (sized for kFwdSlab)
+  FusedWs W = fused_ws(D, slab, ws);
   int nsm; rc = sm_count(&nsm); if (rc) return rc;
   k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
-  const int64_t npairs = (B + 1) / 2;
-  int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
-  if (grid > 4 * nsm) grid = 4 * nsm;
   const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
   cudaError_t e = cudaFuncSetAttribute(k_forward<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_forward<kFusedH><<<grid, P1_THREADS, smem, st>>>(X, idx, B, D->d_pad, D->k, W.pw, y);
+  for (int64_t b0 = 0; b0 < B; b0 += kFwdSlab) {
+    const int64_t bc = (B - b0 < kFwdSlab) ? B - b0 : kFwdSlab;
+    // identity indexing: shift the base pointer; explicit indices: shift the index pointer
+    e = launch_gather(D, idx ? X : X + b0 * D->d_pad, nullptr, idx ? idx + b0 : nullptr, bc, W.xt, W.wt, st);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t npairs = (bc + 1) / 2;
+    int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
+    if (grid > 4 * nsm) grid = 4 * nsm;
+    k_forward<kFusedH><<<grid, P1_THREADS, smem, st>>>(W.xt, bc, D->d, D->d_pad, D->k, W.pw, y + b0 * D->k);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -83,6 +83,15 @@ __device__ __forceinline__ void bias2(const float* __restrict__ sb, float2 (&y)[
   }
 }
 
+// Global loads through volatile asm: issued exactly where written (the compiler otherwise sinks
+// them next to their first use, which exposes the full memory latency with one warp per scheduler).
+// (64-bit register outputs so that the value stays an aligned register pair for FFMA2.)
+__device__ __forceinline__ float2 ldg_early2(const float2* p) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return *reinterpret_cast<float2*>(&v);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,8 +19,11 @@ template <int H>
 struct PackLayout {
   int d_pad;
   __host__ __device__ explicit PackLayout(int dp) : d_pad(dp) {}
-  __host__ __device__ int W1c() const { return 0; }                 // [d_pad/4][H][4]: W1[o][4*j4+q]
-  __host__ __device__ int b1() const { return d_pad * H; }
+  // W1T[j][o] = W1[o][j]; rows j >= d are zero and the row count is padded to a multiple of 16 so
+  // that the unguarded 8- / 16-column blocks of layer 1 never leave the array
+  __host__ __device__ int w1rows() const { return (d_pad + 15) / 16 * 16; }
+  __host__ __device__ int W1c() const { return 0; }
+  __host__ __device__ int b1() const { return w1rows() * H; }
   __host__ __device__ int W2T() const { return b1() + H; }          // [i][o] = W2[o][i]
   __host__ __device__ int W2() const { return W2T() + H * H; }      // [o][i]
   __host__ __device__ int b2() const { return W2() + H * H; }
@@ -72,8 +75,8 @@ __global__ void k_pack(const float* __restrict__ params, const float* __restrict
   const float* b3 = W3 + H * H;
   const float* W4 = b3 + H;
   const float* b4 = W4 + H;
-  for (int e = threadIdx.x; e < d_pad * H; e += blockDim.x) {
-    const int q = e & 3, oo = (e >> 2) % H, j4 = (e >> 2) / H, j = 4 * j4 + q;
+  for (int e = threadIdx.x; e < L.w1rows() * H; e += blockDim.x) {
+    const int oo = e % H, j = e / H;
     o[L.W1c() + e] = (j < d) ? W1[oo * d + j] : 0.f;
   }
   for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
@@ -95,63 +98,76 @@ __global__ void k_pack(const float* __restrict__ params, const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // shared pieces of the per-sample-pair computation
 // ---------------------------------------------------------------------------------------------
-// layer 1: z1 = W1 x + b1 with x read straight from the (gathered) global rows.  FFMA2 lanes
-// pair neighbouring input columns here (natural register pairs of the float4 row loads); the
-// two partial sums are added at the end.  a1 = tanh(z1) as a sample pair.
-template <int H>
-__device__ __forceinline__ void l1_chunk(const float* __restrict__ wrow, const float4 xa, const float4 xb,
-                                         float2 (&s0)[H], float2 (&s1)[H]) {
-#pragma unroll
-  for (int o = 0; o < H; o++) {
-    const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o);
-    s0[o] = ffma2(make_float2(w.x, w.y), make_float2(xa.x, xa.y), s0[o]);
-    s1[o] = ffma2(make_float2(w.x, w.y), make_float2(xb.x, xb.y), s1[o]);
-    s0[o] = ffma2(make_float2(w.z, w.w), make_float2(xa.z, xa.w), s0[o]);
-    s1[o] = ffma2(make_float2(w.z, w.w), make_float2(xb.z, xb.w), s1[o]);
+// ---------------------------------------------------------------------------------------------
+// k_gather: X[idx[n]][:] -> tile-major TRANSPOSED copy  xt[tile][j][256]  (+ wt[n] = w[idx[n]])
+// ---------------------------------------------------------------------------------------------
+// Row gathers by random indices are expensive inside the compute kernels (a warp-wide LDG.128
+// over 32 different rows touches 32 cache lines); here each row is read once, cooperatively and
+// coalesced, transposed through shared memory, and written so that a sample pair's x_j is ONE
+// coalesced 8-byte load and a tile's row j is 1 KB contiguous (the layout of the k_pass2 rows).
+constexpr int GT = 256;                       // samples per tile (= P2_T)
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256)
+k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+         int d_pad, float* __restrict__ xt, float* __restrict__ wt) {
+  extern __shared__ float4 smem4[];
+  float* ts = reinterpret_cast<float*>(smem4);           // [256][d_pad + 1]
+  __shared__ int64_t srow[GT];
+  const int ld = d_pad + 1, nq = d_pad >> 2, t = threadIdx.x;
+  const int64_t tile = blockIdx.x, n = tile * GT + t;
+  const bool v = n < B;
+  const int64_t r = v ? (idx ? idx[n] : n) : 0;
+  srow[t] = v ? r : -1;
+  wt[n] = v ? (w ? w[r] : 1.f) : 0.f;
+  __syncthreads();
+  for (int c = t; c < GT * nq; c += 256) {
+    const int row = c / nq, q = c - row * nq;
+    const int64_t rr = srow[row];
+    const float4 val = (rr >= 0) ? __ldg(reinterpret_cast<const float4*>(X + rr * d_pad) + q)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dst = ts + row * ld + 4 * q;
+    dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
   }
+  __syncthreads();
+  float* out = xt + (size_t)tile * d_pad * GT;
+  for (int j = 0; j < d_pad; j++) out[(size_t)j * GT + t] = ts[t * ld + j];
 }
 
-template <int H>
-__device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1c, const float* __restrict__ sb1,
-                                           const float* __restrict__ xr0, const float* __restrict__ xr1, int nj4,
-                                           float2 (&a1)[H]) {
-  float2 s0[H], s1[H];
-  zero2(s0); zero2(s1);
-  // The rows are gathered (random) global reads: keep one group of four float4 per row in
-  // flight ahead of the FFMA2 stream (software pipeline, distance = 4 chunks ~ 640 FMA cycles).
-  constexpr int PF = 4;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 ca[PF], cb[PF];
+// layer 1: a1 = tanh(W1 x + b1); x_j of the sample pair is one coalesced float2 of the transposed
+// tile, software-pipelined PF columns ahead of the FFMA2 stream.
+template <int H, int PF = 8>
+__device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1T, const float* __restrict__ sb1,
+                                           const float* __restrict__ xcol, int d, int d_pad, float2 (&a1)[H]) {
+  bias2<H>(sb1, a1);
+  float2 cur[PF];
 #pragma unroll
-  for (int q = 0; q < PF; q++) {
-    ca[q] = (q < nj4) ? __ldg(reinterpret_cast<const float4*>(xr0) + q) : z4;
-    cb[q] = (q < nj4) ? __ldg(reinterpret_cast<const float4*>(xr1) + q) : z4;
-  }
+  for (int q = 0; q < PF; q++)
+    cur[q] = __ldg(reinterpret_cast<const float2*>(xcol + (size_t)(q < d_pad ? q : d_pad - 1) * GT));
 #pragma unroll 1
-  for (int j0 = 0; j0 < nj4; j0 += PF) {
-    float4 na[PF], nb[PF];
+  for (int j0 = 0; j0 < d; j0 += PF) {
+    float2 nxt[PF];
+#pragma unroll
+    for (int q = 0; q < PF; q++) {     // clamped address: columns >= d meet zero weight rows
+      const int j = j0 + PF + q;
+      nxt[q] = __ldg(reinterpret_cast<const float2*>(xcol + (size_t)(j < d_pad ? j : d_pad - 1) * GT));
+    }
 #pragma unroll
     for (int q = 0; q < PF; q++) {
-      const int j = j0 + PF + q;
-      na[q] = (j < nj4) ? __ldg(reinterpret_cast<const float4*>(xr0) + j) : z4;
-      nb[q] = (j < nj4) ? __ldg(reinterpret_cast<const float4*>(xr1) + j) : z4;
+      const float* wr = sW1T + (j0 + q) * H;
+#pragma unroll
+      for (int c = 0; c < H / 4; c++) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * c);
+        a1[4 * c + 0] = ffma2(splat(wv.x), cur[q], a1[4 * c + 0]);
+        a1[4 * c + 1] = ffma2(splat(wv.y), cur[q], a1[4 * c + 1]);
+        a1[4 * c + 2] = ffma2(splat(wv.z), cur[q], a1[4 * c + 2]);
+        a1[4 * c + 3] = ffma2(splat(wv.w), cur[q], a1[4 * c + 3]);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < PF; q++)
-      if (j0 + q < nj4) l1_chunk<H>(sW1c + (j0 + q) * (H * 4), ca[q], cb[q], s0, s1);
-#pragma unroll
-    for (int q = 0; q < PF; q++) { ca[q] = na[q]; cb[q] = nb[q]; }
+    for (int q = 0; q < PF; q++) cur[q] = nxt[q];
   }
 #pragma unroll
-  for (int q = 0; q < H / 4; q++) {
-    const float4 b = *reinterpret_cast<const float4*>(sb1 + 4 * q);
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const int o = 4 * q + r;
-      a1[o] = tanh2(make_float2(s0[o].x + s0[o].y + bb[r], s1[o].x + s1[o].y + bb[r]));
-    }
-  }
+  for (int o = 0; o < H; o++) a1[o] = tanh2(a1[o]);
 }
 
 // hidden layer: a_out = tanh(W a_in + b), weights in [in][out] layout
@@ -213,8 +229,8 @@ constexpr int P1_THREADS = 256;
 
 template <int H, int K>
 __global__ void __launch_bounds__(P1_THREADS, 1)
-k_pass1(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
-        int d_pad, const float* __restrict__ pw, float* __restrict__ ybuf, double* __restrict__ part) {
+k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad,
+        const float* __restrict__ pw, float* __restrict__ ybuf, double* __restrict__ part) {
   constexpr int NS = 1 + 2 * K + K * (K + 1) / 2;
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
@@ -228,21 +244,18 @@ k_pass1(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
   for (int s = 0; s < NS; s++) acc[s] = 0.0;
 
   const int64_t npairs = (B + 1) >> 1;
-  const int nj4 = d_pad >> 2;
   for (int64_t p = (int64_t)blockIdx.x * P1_THREADS + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * P1_THREADS) {
     const int64_t n0 = 2 * p, n1 = 2 * p + 1;
     const bool v1 = n1 < B;
-    const int64_t r0 = idx ? idx[n0] : n0;
-    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
-    const float w0 = w[r0], w1 = v1 ? w[r1] : 0.f;
-    const float* xr0 = X + r0 * d_pad;
-    const float* xr1 = X + r1 * d_pad;
+    const float2 w01 = __ldg(reinterpret_cast<const float2*>(wt + n0));     // wt is padded to whole tiles
+    const float w0 = w01.x, w1 = w01.y;
+    const float* xcol = xt + (size_t)(n0 / GT) * d_pad * GT + (n0 % GT);
     float2 yv[K], ev[K];
 #pragma unroll 1
     for (int net = 0; net < K; net++) {
       const float* s = sw + net * pwn;
       float2 a1[H], a2[H], a3[H], g[H], u[H];
-      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xr0, xr1, nj4, a1);
+      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1);
       fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
       fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a3);
       const float2 y = fwd_out<H>(s + L.w4(), s + L.b4(), a3);
@@ -292,6 +305,15 @@ k_pass1(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
 // ---------------------------------------------------------------------------------------------
 // k_pass2
 // ---------------------------------------------------------------------------------------------
+#ifdef EPDE_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define PHASE_T0() long long pt_ = clock64()
+#define PHASE_ADD(slot) do { long long n_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n_ - pt_)); pt_ = n_; } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot) do {} while (0)
+#endif
+
 constexpr int P2_THREADS = 128;            // 4 warps, one per SM sub-partition
 constexpr int P2_T = 2 * P2_THREADS;       // samples per tile
 constexpr int P2_TS = P2_T + 4;            // row stride (floats): rows start 4 banks apart
@@ -300,8 +322,8 @@ constexpr int P2_NG = 2;                   // sample groups of the outer-product
 // shared-memory row map (rows of P2_TS floats, [feature][sample])
 template <int H>
 struct RowMap {
-  int xr;   // rows reserved for the transposed x tile = 5 * ceil(d / 5)
-  __host__ __device__ explicit RowMap(int d) : xr(5 * ((d + 4) / 5)) {}
+  int xr;   // rows reserved for the transposed x tile = 10 * ceil(d / 10)
+  __host__ __device__ explicit RowMap(int d) : xr(10 * ((d + 9) / 10)) {}
   // region 1
   __host__ __device__ int A1() const { return 0; }
   __host__ __device__ int A2() const { return H; }
@@ -336,45 +358,68 @@ __host__ __device__ inline size_t pass2_smem_bytes(int d, int d_pad) {
 // one 4x5 register tile of an outer product over the samples [n0, n0 + cnt):
 //   out[o][i] += sum_n P[o][n] * Q[i][n],  o in {ot + 5a}, i in {5*it + b}
 // FFMA2 lanes pair neighbouring samples; the two partial sums are added at the end.
-template <bool SCALE>
-__device__ __forceinline__ void outer_unit(const float* __restrict__ prow, const float* __restrict__ qrow,
-                                           const float* __restrict__ eb, int n0, int cnt,
-                                           float* __restrict__ out, int ld, int ot, int it, int imax) {
-  float2 acc[4][5];
+template <bool SCALE, int RI>
+struct OuterOps {
+  float4 p[4], q[RI], s;
+  __device__ __forceinline__ void load(const float* __restrict__ p0, const float* __restrict__ q0,
+                                       const float* __restrict__ e0, int n) {
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 4; a++) p[a] = *reinterpret_cast<const float4*>(p0 + (5 * a) * P2_TS + n);
 #pragma unroll
-    for (int b = 0; b < 5; b++) acc[a][b] = make_float2(0.f, 0.f);
-  const float* p0 = prow + ot * P2_TS + n0;
-  const float* q0 = qrow + (5 * it) * P2_TS + n0;
-#pragma unroll 2
-  for (int n = 0; n < cnt; n += 4) {
-    float4 pv[4], qv[5];
-#pragma unroll
-    for (int a = 0; a < 4; a++) pv[a] = *reinterpret_cast<const float4*>(p0 + (5 * a) * P2_TS + n);
-#pragma unroll
-    for (int b = 0; b < 5; b++) qv[b] = *reinterpret_cast<const float4*>(q0 + b * P2_TS + n);
+    for (int b = 0; b < RI; b++) q[b] = *reinterpret_cast<const float4*>(q0 + b * P2_TS + n);
+    if (SCALE) s = *reinterpret_cast<const float4*>(e0 + n);
+  }
+  __device__ __forceinline__ void mac(float2 (&acc)[4][RI]) {
     if (SCALE) {
-      const float4 s = *reinterpret_cast<const float4*>(eb + n0 + n);
 #pragma unroll
-      for (int a = 0; a < 4; a++) { pv[a].x *= s.x; pv[a].y *= s.y; pv[a].z *= s.z; pv[a].w *= s.w; }
+      for (int a = 0; a < 4; a++) { p[a].x *= s.x; p[a].y *= s.y; p[a].z *= s.z; p[a].w *= s.w; }
     }
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int b = 0; b < 5; b++) {
-        acc[a][b] = ffma2(make_float2(pv[a].x, pv[a].y), make_float2(qv[b].x, qv[b].y), acc[a][b]);
-        acc[a][b] = ffma2(make_float2(pv[a].z, pv[a].w), make_float2(qv[b].z, qv[b].w), acc[a][b]);
+      for (int b = 0; b < RI; b++) {
+        acc[a][b] = ffma2(make_float2(p[a].x, p[a].y), make_float2(q[b].x, q[b].y), acc[a][b]);
+        acc[a][b] = ffma2(make_float2(p[a].z, p[a].w), make_float2(q[b].z, q[b].w), acc[a][b]);
       }
+  }
+};
+
+// one 4 x RI register tile of an outer product over the samples [n0, n0 + cnt), cnt % 8 == 0:
+//   out[o][i] += sum_n P[o][n] * Q[i][n],  o in {ot + 5a}, i in {RI*it + b}
+// FFMA2 lanes pair neighbouring samples (the two partial sums are added at the end).  Two operand
+// buffers alternate so that the loads of step n+4 are in flight while step n is multiplied (one warp
+// per scheduler: nobody else hides the shared-memory latency).
+template <bool SCALE, int RI>
+__device__ __forceinline__ void outer_unit(const float* __restrict__ prow, const float* __restrict__ qrow,
+                                           const float* __restrict__ eb, int n0, int cnt,
+                                           float* __restrict__ out, int ld, int ot, int it, int imax) {
+  float2 acc[4][RI];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < RI; b++) acc[a][b] = make_float2(0.f, 0.f);
+  const float* p0 = prow + ot * P2_TS + n0;
+  const float* q0 = qrow + (RI * it) * P2_TS + n0;
+  const float* e0 = SCALE ? eb + n0 : nullptr;
+  OuterOps<SCALE, RI> A, B;
+  A.load(p0, q0, e0, 0);
+#pragma unroll 1
+  for (int n = 0; n < cnt; n += 8) {
+    B.load(p0, q0, e0, n + 4);
+    A.mac(acc);
+    A.load(p0, q0, e0, (n + 8 < cnt) ? n + 8 : n);     // last iteration: harmless reload
+    B.mac(acc);
   }
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
-    for (int b = 0; b < 5; b++) {
-      const int i = 5 * it + b;
+    for (int b = 0; b < RI; b++) {
+      const int i = RI * it + b;
       if (i < imax) out[(ot + 5 * a) * ld + i] += acc[a][b].x + acc[a][b].y;
     }
 }
+
+__device__ __forceinline__ void prefetch_l2g(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // sum of one row over the tile -> out
 __device__ __forceinline__ void row_sum(const float* __restrict__ row, float* __restrict__ out) {
@@ -389,7 +434,7 @@ __device__ __forceinline__ void row_sum(const float* __restrict__ row, float* __
 
 template <int H>
 __global__ void __launch_bounds__(P2_THREADS, 1)
-k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
         int d, int d_pad, int K, const float* __restrict__ pw, const float* __restrict__ ybuf,
         const Coef* __restrict__ coef, float* __restrict__ pg) {
   static_assert(H == 20, "outer-product tiling (4x5 tiles, row stride 5) is written for H = 20");
@@ -419,30 +464,45 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
   const int64_t ntiles = (B + P2_T - 1) / P2_T;
 #define ROW2(r) (*reinterpret_cast<float2*>(rows + (r) * P2_TS + col))
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // Per-tile scalars (sample weights, ybar seed): loaded for tile t+1 at the start of GM2 of tile t,
+  // combined at its end -- no global-load latency at the top of a tile.
+  float2 c_wn = make_float2(0.f, 0.f), c_ybar = make_float2(0.f, 0.f);
+  float2 p_w = make_float2(0.f, 0.f);
+  float p_y0[8], p_y1[8];
+  auto stage_b = [&](int64_t tile) {
     const int64_t n0 = tile * P2_T + col, n1 = n0 + 1;
     const bool v0 = n0 < B, v1 = n1 < B;
-    const int64_t r0 = v0 ? (idx ? idx[n0] : n0) : 0;
-    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
-    const float2 wn = make_float2(v0 ? w[r0] : 0.f, v1 ? w[r1] : 0.f);
-    const float* xr0 = X + r0 * d_pad;
-    const float* xr1 = X + r1 * d_pad;
+    p_w = __ldg(reinterpret_cast<const float2*>(wt + n0));          // 0 for samples beyond B
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      p_y0[j] = (j < K && v0) ? ybuf[n0 * K + j] : 0.f;
+      p_y1[j] = (j < K && v1) ? ybuf[n1 * K + j] : 0.f;
+    }
+  };
+  auto stage_c = [&]() {
+    float s0 = -cm, s1 = -cm;                       // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
+#pragma unroll
+    for (int j = 0; j < 8; j++) { s0 = fmaf(cw[j], p_y0[j], s0); s1 = fmaf(cw[j], p_y1[j], s1); }
+    c_wn = p_w;
+    c_ybar = make_float2(p_w.x * s0, p_w.y * s1);
+  };
+  if ((int64_t)blockIdx.x < ntiles) { stage_b(blockIdx.x); stage_c(); }
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float2 wn = c_wn;
+    const float* xtile = xt + (size_t)tile * d_pad * GT;
+    const int64_t next_tile = tile + gridDim.x;
+    const bool has_next = next_tile < ntiles;
     float2 ze1[H], ze2[H];
 
+    PHASE_T0();
     // ================= MV1: forward, Jacobian chain, first reverse sweep ====================
     {
-      float2 ybar;
-      {   // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
-        float s0 = -cm, s1 = -cm;
-        for (int j = 0; j < K; j++) {
-          s0 = fmaf(cw[j], v0 ? ybuf[n0 * K + j] : 0.f, s0);
-          s1 = fmaf(cw[j], v1 ? ybuf[n1 * K + j] : 0.f, s1);
-        }
-        ybar = make_float2(wn.x * s0, wn.y * s1);
-      }
+      const float2 ybar = c_ybar;
       const float2 ebar = make_float2(wn.x * ecoef, wn.y * ecoef);
       float2 a[H], g[H], u[H];
-      fwd_layer1<H>(sw + L.W1c(), sw + L.b1(), xr0, xr1, nj4, a);
+      // layer 1: x columns software-pipelined 16 ahead (one warp per scheduler: deeper than k_pass1)
+      fwd_layer1<H, 16>(sw + L.W1c(), sw + L.b1(), xtile + col, d, d_pad, a);
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.A1() + o) = a[o];
       fwd_hidden<H>(sw + L.W2T(), sw + L.b2(), a, g);                  // g := a2
@@ -502,7 +562,9 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
       }
       ROW2(R.YB()) = ybar;
     }
+    PHASE_ADD(0);
     __syncthreads();
+    PHASE_ADD(1);
 
     // ================= GM1: Gamma, and the g (x) ubar parts of dW2, dW3 ======================
     // Every work item runs the same code (no divergence inside a warp): only pointers differ.
@@ -516,14 +578,27 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
         const int qrow = (job == 0) ? R.G1() : (job == 1) ? R.U1() : R.U2();
         const int srow = (job == 0) ? R.EB() : R.ONE();
         const int oo = (job == 0) ? G.Gam() : (job == 1) ? G.gW2() : G.gW3();
-        outer_unit<true>(rows + prow * P2_TS, rows + qrow * P2_TS, rows + srow * P2_TS, grp * SG, SG,
-                         accS + grp * gn + oo, H, t % 5, t / 5, H);
+        outer_unit<true, 5>(rows + prow * P2_TS, rows + qrow * P2_TS, rows + srow * P2_TS, grp * SG, SG,
+                            accS + grp * gn + oo, H, t % 5, t / 5, H);
       }
     }
+    PHASE_ADD(2);
     __syncthreads();
+    PHASE_ADD(3);
 
     // ================= MV2: second reverse sweep, x tile (transposed) ========================
     {
+      // The x tile is the right operand of dW1 = zbar1 (x) x: its rows (1 KB contiguous in the
+      // transposed copy) go straight from global to the shared-memory rows freed by GM1 with
+      // cp.async (no registers); the copies complete behind the two mat-vecs of this phase.
+      {
+        const int nchunk = d * (GT / 4);                               // 16-byte chunks of the tile
+        for (int c = tid; c < nchunk; c += P2_THREADS) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(rows + (R.XT() + (c >> 6)) * P2_TS + 4 * (c & 63));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(xtile) + c));
+        }
+        asm volatile("cp.async.commit_group;");
+      }
       float2 z[H], t[H];
 #pragma unroll
       for (int o = 0; o < H; o++) z[o] = ROW2(R.Z3() + o);
@@ -542,35 +617,32 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
         const float2 dd = ffma2(make_float2(-a1.x, -a1.y), a1, splat(1.0f));
         ROW2(R.Z1() + o) = ffma2(dd, t[o], ze1[o]);                    // zbar1
       }
-#pragma unroll 1
-      for (int j4 = 0; j4 < nj4; j4++) {
-        const float4 xa = __ldg(reinterpret_cast<const float4*>(xr0) + j4);
-        const float4 xb = __ldg(reinterpret_cast<const float4*>(xr1) + j4);
-        const int j = 4 * j4;
-        if (j + 0 < R.xr) ROW2(R.XT() + j + 0) = make_float2(xa.x, xb.x);
-        if (j + 1 < R.xr) ROW2(R.XT() + j + 1) = make_float2(xa.y, xb.y);
-        if (j + 2 < R.xr) ROW2(R.XT() + j + 2) = make_float2(xa.z, xb.z);
-        if (j + 3 < R.xr) ROW2(R.XT() + j + 3) = make_float2(xa.w, xb.w);
-      }
-      for (int j = 4 * nj4; j < R.xr; j++) ROW2(R.XT() + j) = make_float2(0.f, 0.f);
+      for (int j = d; j < R.xr; j++) ROW2(R.XT() + j) = make_float2(0.f, 0.f);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    PHASE_ADD(4);
     __syncthreads();
+    PHASE_ADD(5);
 
     // ================= GM2: zbar (x) [x | a1 | a2], bias and w4 row sums =====================
+    if (has_next) stage_b(next_tile);
     {
-      constexpr int UPJ = (H / 4) * (H / 5);
-      const int njt = R.xr / 5;
+      // 4x10 register tiles (14 LDS.128 per 80 FFMA2), two sample groups of 128
+      constexpr int UPJ = (H / 4) * (H / 10);
+      constexpr int SG = P2_T / P2_NG;
+      const int njt = R.xr / 10;
       const int nu1 = 5 * njt;                   // (H/4) * njt units for dW1
-      const int NU = nu1 + 2 * UPJ;
+      const int NU = (nu1 + 2 * UPJ) * P2_NG;
       for (int wk = tid; wk < NU; wk += P2_THREADS) {
-        const int job = (wk < nu1) ? 0 : (wk < nu1 + UPJ) ? 1 : 2;
-        const int t = (job == 0) ? wk : (job == 1) ? wk - nu1 : wk - nu1 - UPJ;
+        const int grp = wk / (NU / P2_NG), un = wk % (NU / P2_NG);
+        const int job = (un < nu1) ? 0 : (un < nu1 + UPJ) ? 1 : 2;
+        const int t = (job == 0) ? un : (job == 1) ? un - nu1 : un - nu1 - UPJ;
         const int prow = (job == 0) ? R.Z1() : (job == 1) ? R.Z2() : R.Z3();
         const int qrow = (job == 0) ? R.XT() : (job == 1) ? R.A1() : R.A2();
         const int oo = (job == 0) ? G.gW1() : (job == 1) ? G.gW2() : G.gW3();
         const int ld = (job == 0) ? d_pad : H, imax = (job == 0) ? d : H;
-        outer_unit<false>(rows + prow * P2_TS, rows + qrow * P2_TS, nullptr, 0, P2_T, accS + oo, ld, t % 5, t / 5,
-                          imax);
+        outer_unit<false, 10>(rows + prow * P2_TS, rows + qrow * P2_TS, nullptr, grp * SG, SG,
+                              accS + grp * gn + oo, ld, t % 5, t / 5, imax);
       }
       const int nrows = 4 * H + 1;               // bias / w4 row sums on the threads without a unit
       const int first = (NU < P2_THREADS) ? NU : 0, nfree = P2_THREADS - first;
@@ -583,7 +655,10 @@ k_pass2(const float* __restrict__ X, const float* __restrict__ w, const int64_t*
         row_sum(rows + srow * P2_TS, accS + oo);
       }
     }
+    if (has_next) stage_c();
+    PHASE_ADD(6);
     __syncthreads();
+    PHASE_ADD(7);
   }
 #undef ROW2
   float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;
@@ -635,7 +710,7 @@ __global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int
 // forward only: y[B][K]
 template <int H>
 __global__ void __launch_bounds__(P1_THREADS, 1)
-k_forward(const float* __restrict__ X, const int64_t* __restrict__ idx, int64_t B, int d_pad, int K,
+k_forward(const float* __restrict__ xt, int64_t B, int d, int d_pad, int K,
           const float* __restrict__ pw, float* __restrict__ y) {
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
@@ -644,17 +719,15 @@ k_forward(const float* __restrict__ X, const int64_t* __restrict__ idx, int64_t 
   for (int i = threadIdx.x; i < K * pwn; i += P1_THREADS) sw[i] = pw[i];
   __syncthreads();
   const int64_t npairs = (B + 1) >> 1;
-  const int nj4 = d_pad >> 2;
   for (int64_t p = (int64_t)blockIdx.x * P1_THREADS + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * P1_THREADS) {
     const int64_t n0 = 2 * p, n1 = 2 * p + 1;
     const bool v1 = n1 < B;
-    const int64_t r0 = idx ? idx[n0] : n0;
-    const int64_t r1 = v1 ? (idx ? idx[n1] : n1) : r0;
+    const float* xcol = xt + (size_t)(n0 / GT) * d_pad * GT + (n0 % GT);
 #pragma unroll 1
     for (int net = 0; net < K; net++) {
       const float* s = sw + net * pwn;
       float2 a1[H], a2[H];
-      fwd_layer1<H>(s + L.W1c(), s + L.b1(), X + r0 * d_pad, X + r1 * d_pad, nj4, a1);
+      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1);
       fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
       fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a1);
       const float2 yy = fwd_out<H>(s + L.w4(), s + L.b4(), a1);

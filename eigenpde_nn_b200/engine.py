@@ -137,7 +137,7 @@ class StepEngine:
                     var=h[4 + 3 * k:4 + 4 * k].copy(), grad=grad)
 
     def forward(self, idx_dev, B, params_dev):
-        ws = self._workspace(max(B, 1))
+        ws = self._workspace(max(min(B, 262144), 1))
         y = torch.empty((B, self.k), dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self.lib.epde_forward(C.byref(self.desc), _ptr(self.X), _ptr(idx_dev), C.c_int64(B),

@@ -135,8 +135,8 @@ int epde_step(const epde_desc* desc, const float* d_X, const float* d_w, const i
 /*
  * Forward only: y[B][k] = MyNet.forward on the selected rows (src/network_arch.py:108-117),
  * used by the stage-end re-normalisation (src/pytorch_eigen_solver.py:120-141) and by
- * utils/eval_nn_on_*.py.  d_y is fp32 [B][k] row-major.  The workspace only has to be
- * epde_workspace_bytes(desc, 1) large (it holds the packed weights).
+ * utils/eval_nn_on_*.py.  d_y is fp32 [B][k] row-major.  The samples are processed in slabs of at
+ * most 2^18, so the workspace has to be epde_workspace_bytes(desc, min(B, 262144)) large.
  */
 int epde_forward(const epde_desc* desc, const float* d_X, const int64_t* d_idx, int64_t B,
                  const float* d_params, const float* d_diag_coeff, void* d_workspace, size_t workspace_bytes,

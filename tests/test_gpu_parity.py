@@ -110,11 +110,11 @@ def test_ragged_batch_sizes_vs_oracle(B):
     _check(c, _oracle(c), res)
 
 
-@pytest.mark.parametrize("d,k", [(1, 1), (2, 2), (3, 2), (5, 4), (30, 2), (49, 3), (50, 6), (52, 5), (64, 3), (90, 2)])
+@pytest.mark.parametrize("d,k", [(1, 1), (2, 2), (3, 2), (5, 4), (30, 2), (49, 3), (50, 6), (52, 5), (60, 3), (64, 3), (90, 2)])
 def test_dims_and_net_counts_vs_oracle(d, k):
     c = _rand_case(7 * d + k, d, k, [20, 20, 20], 2000, 700, scale=0.4)
     eng = _engine(c)
-    assert eng.fused == (d <= 64)            # d = 90 exceeds the shared-memory budget of the fused tile
+    assert eng.fused == (d <= 60)            # beyond d = 60 the tile state exceeds 227 KB of shared memory
     _check(c, _oracle(c), eng.step(c["idx"], _flat(c["params"]), c["alpha"]))
 
 
