@@ -12,6 +12,7 @@
 
 #include "../../include/eigenpde_b200.h"
 #include "epde_coef.cuh"
+#include "epde_tc_gemm.cuh"
 
 namespace epde {
 
@@ -119,14 +120,21 @@ __global__ void g_jacmul(int act, int64_t n, const float* __restrict__ Z, const 
   if (e >= n) return;
   float v, d1, d2; act_eval(act, Z[e], v, d1, d2); Gout[e] = d1 * U[e];
 }
+// Wp[r][c] = c < cols ? W[r][c] : 0   (row length padded to ldp)
+__global__ void g_pad_weights(int rows, int cols, int ldp, const float* __restrict__ W, float* __restrict__ Wp) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * ldp) return;
+  const int r = e / ldp, c = e % ldp;
+  Wp[e] = (c < cols) ? W[(size_t)r * cols + c] : 0.f;
+}
 // e[b] = sum_j c_j U0[b][j]^2 ; y[b] -> ybuf / ebuf columns of net `net`
-__global__ void g_energy(int Bc, int d, const float* __restrict__ U0, const float* __restrict__ c,
+__global__ void g_energy(int Bc, int d, int ldu, const float* __restrict__ U0, const float* __restrict__ c,
                          const float* __restrict__ ycol, int64_t b0, int k, int net, float* __restrict__ ybuf,
                          float* __restrict__ ebuf) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= Bc) return;
   float s = 0.f;
-  for (int j = 0; j < d; j++) { const float u = U0[(size_t)b * d + j]; s = fmaf(c[j] * u, u, s); }
+  for (int j = 0; j < d; j++) { const float u = U0[(size_t)b * ldu + j]; s = fmaf(c[j] * u, u, s); }
   ebuf[(b0 + b) * k + net] = s;
   ybuf[(b0 + b) * k + net] = ycol[b];
 }
@@ -164,14 +172,14 @@ __global__ void g_reduce_part(const double* __restrict__ part, int nb, int ns, d
   sums[s] = v;
 }
 // Ubar_0 = 2 c (.) U_0 * ebar,  ebar = w_n * ecoef[net]
-__global__ void g_seed(int Bc, int d, const float* __restrict__ U0, const float* __restrict__ c,
+__global__ void g_seed(int Bc, int d, int ldu, const float* __restrict__ U0, const float* __restrict__ c,
                        const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t b0,
                        const Coef* __restrict__ coef, int net, float* __restrict__ Ub) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (int64_t)Bc * d) return;
-  const int b = (int)(e / d), j = (int)(e % d);
+  if (e >= (int64_t)Bc * ldu) return;
+  const int b = (int)(e / ldu), j = (int)(e % ldu);
   const float eb = w[idx ? idx[b0 + b] : b0 + b] * coef->ecoef[net];
-  Ub[e] = 2.f * c[j] * U0[e] * eb;
+  Ub[e] = (j < d) ? 2.f * c[j] * U0[e] * eb : 0.f;          // padding columns stay zero
 }
 // Ubar_l = phi'(Z_l) Gbar_l ; Zbar_l = phi''(Z_l) U_l Gbar_l
 __global__ void g_esweep(int act, int64_t n, const float* __restrict__ Z, const float* __restrict__ U,
@@ -199,6 +207,15 @@ __global__ void g_ybar(int Bc, int k, int net, const float* __restrict__ w, cons
   for (int j = 0; j < k; j++) s = fmaf(coef->Cw[net][j], ybuf[(b0 + b) * k + j], s);
   ZL[b] = w[idx ? idx[b0 + b] : b0 + b] * s;
 }
+// dacc[c] += sum_r Zb[r][c]  (bias gradients): coalesced column sums, fp64 per thread, one atomic per block
+__global__ void g_colsum(int rows, int n, const float* __restrict__ Zb, double* __restrict__ dacc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  double s = 0.0;
+  for (int r = r0; r < r1; r++) s += (double)Zb[(size_t)r * n + c];
+  atomicAdd(&dacc[c], s);
+}
 __global__ void g_zero_d(int64_t n, double* __restrict__ o) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) o[e] = 0.0;
@@ -211,12 +228,15 @@ __global__ void g_to_float(int64_t n, const double* __restrict__ a, float* __res
 // ---- host orchestration ----------------------------------------------------------------------
 struct GenericPlan {
   int L; int n[EPDE_MAX_LAYERS + 1]; int maxn; int sumh;   // sumh = sum of hidden widths
+  int w[EPDE_MAX_LAYERS + 1];                              // buffer / GEMM widths: w[0] = d_pad, w[l] = n[l]
+  float* wp; int64_t wp_net;                               // 16-byte aligned, column-padded weight copies
   int64_t Bc;                                              // chunk size
   // workspace pointers
   float *ybuf, *ebuf, *Xc, *U0, *Ub, *Gb, *T, *ones;
   float *Z[EPDE_MAX_LAYERS + 1], *A[EPDE_MAX_LAYERS + 1], *G[EPDE_MAX_LAYERS + 1], *U[EPDE_MAX_LAYERS + 1],
       *Zb[EPDE_MAX_LAYERS + 1];
   double *part, *gacc; Coef* coef;
+  float* cpart; size_t cpart_floats;                      // split-K partial tiles of the tcgen05 GEMM
   size_t total;
 };
 
@@ -226,8 +246,11 @@ inline GenericPlan generic_plan(const epde_desc* D, int64_t B, void* base) {
   GenericPlan P; P.L = D->n_layers; P.maxn = D->d_pad; P.sumh = 0;
   for (int l = 0; l <= P.L; l++) { P.n[l] = D->widths[l]; if (P.n[l] > P.maxn) P.maxn = P.n[l]; }
   for (int l = 1; l < P.L; l++) P.sumh += P.n[l];
+  for (int l = 0; l <= P.L; l++) P.w[l] = (l == 0) ? D->d_pad : P.n[l];
+  P.wp_net = 0;
+  for (int l = 1; l <= P.L; l++) P.wp_net += ((int64_t)P.n[l] * P.w[l - 1] + 3) / 4 * 4;
   const size_t per_sample = (size_t)4 * (5 * (P.sumh + 1) + 3 * P.maxn + 2 * D->d_pad + 4);
-  int64_t bc = (int64_t)((size_t)(192u << 20) / per_sample);
+  int64_t bc = (int64_t)((size_t)(1536u << 20) / per_sample);      // <= 1.5 GB of per-chunk matrices
   bc = bc / 256 * 256; if (bc < 256) bc = 256; if (bc > 65536) bc = 65536;
   if (bc > B) bc = B;
   P.Bc = bc;
@@ -239,12 +262,16 @@ inline GenericPlan generic_plan(const epde_desc* D, int64_t B, void* base) {
   P.part = (double*)take((size_t)256 * (1 + 2 * EPDE_MAX_K + EPDE_MAX_K * (EPDE_MAX_K + 1) / 2) * 8);
   P.coef = (Coef*)take(sizeof(Coef));
   P.gacc = (double*)take((size_t)pc * D->k * 8);
+  P.wp = (float*)take((size_t)P.wp_net * D->k * 4);
   P.Xc = (float*)take((size_t)bc * D->d_pad * 4);
-  P.U0 = (float*)take((size_t)bc * D->d * 4);
+  P.U0 = (float*)take((size_t)bc * D->d_pad * 4);
   P.Ub = (float*)take((size_t)bc * P.maxn * 4);
   P.Gb = (float*)take((size_t)bc * P.maxn * 4);
   P.T = (float*)take((size_t)bc * P.maxn * 4);
   P.ones = (float*)take((size_t)bc * 4);
+  P.cpart_floats = (size_t)64 * P.maxn * P.maxn;
+  if (P.cpart_floats > ((size_t)16 << 20)) P.cpart_floats = (size_t)16 << 20;
+  P.cpart = (float*)take(P.cpart_floats * 4);
   for (int l = 1; l <= P.L; l++) {
     P.Z[l] = (float*)take((size_t)bc * P.n[l] * 4);
     P.A[l] = (float*)take((size_t)bc * P.n[l] * 4);
@@ -263,44 +290,90 @@ inline int generic_workspace_bytes(const epde_desc* D, int64_t B, size_t* out) {
 
 inline unsigned g_blocks(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+struct TcCtx { float* cpart; size_t cap; };
+
+// C = op(A) op(B) (+bias) or, with dacc, dacc += op(A) op(B) in fp64.
+// Large, 16-byte-aligned products go to the tcgen05 3xTF32 kernel; the rest to the FFMA tile kernel.
 template <bool TA, bool TB>
-inline void gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-                 int ldc, const float* bias, double* dacc) {
+inline void gemm(cudaStream_t st, const TcCtx& tc, int M, int N, int K, const float* A, int lda, const float* B,
+                 int ldb, float* C, int ldc, const float* bias, double* dacc, int n_valid = -1) {
+  // n_valid (dacc mode): only the first n_valid of the N output columns are accumulated (N is the
+  // zero-padded width of the operands); the accumulator has leading dimension ldc.
+  if (n_valid < 0) n_valid = N;
+  const bool aligned = !(lda & 3) && !(ldb & 3) && !((uintptr_t)A & 15) && !((uintptr_t)B & 15) &&
+                       (TA ? !(M & 3) : !(K & 3)) && (TB ? !(K & 3) : !(N & 3));
+  const bool big = M >= 64 && N >= 16 && K >= 32 && (double)M * N * K >= 4.0e6;
+  if (aligned && big && tc.cpart) {
+    cudaFuncSetAttribute(g_gemm_tc<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN;
+    if (!dacc) {
+      g_gemm_tc<TA, TB><<<dim3(nt, mt, 1), TC_THREADS, TC_SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, K, 0);
+    } else {
+      // split K over enough CTAs to fill the chip; partial tiles in fp32, summed into fp64 afterwards
+      int nz = (160 + mt * nt - 1) / (mt * nt);
+      const int maxz = (K + 255) / 256;
+      if (nz > maxz) nz = maxz;
+      if (nz > 64) nz = 64;
+      while (nz > 1 && (size_t)nz * M * N > tc.cap) nz--;
+      int ksplit = ((K + nz - 1) / nz + TC_BK - 1) / TC_BK * TC_BK;
+      nz = (K + ksplit - 1) / ksplit;
+      g_gemm_tc<TA, TB><<<dim3(nt, mt, nz), TC_THREADS, TC_SMEM, st>>>(M, N, K, A, lda, B, ldb, tc.cpart, N, nullptr,
+                                                                        ksplit, (size_t)M * N);
+      g_reduce_splits<<<g_blocks((int64_t)M * n_valid), 256, 0, st>>>(tc.cpart, nz, M, N, n_valid, (size_t)M * N, dacc,
+                                                                       ldc);
+    }
+    return;
+  }
   int ksplit = K, nz = 1;
-  if (dacc) { ksplit = 2048; nz = (K + ksplit - 1) / ksplit; }
+  if (dacc) { ksplit = 256; nz = (K + ksplit - 1) / ksplit; N = n_valid; }
   dim3 grid((N + GB - 1) / GB, (M + GB - 1) / GB, nz);
   g_gemm<TA, TB><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, dacc, ksplit);
 }
 
-struct NetParams { const float* W[EPDE_MAX_LAYERS + 1]; const float* b[EPDE_MAX_LAYERS + 1]; int64_t off[EPDE_MAX_LAYERS + 1]; int64_t size; };
+struct NetParams {
+  const float* W[EPDE_MAX_LAYERS + 1]; const float* b[EPDE_MAX_LAYERS + 1]; int64_t off[EPDE_MAX_LAYERS + 1];
+  const float* Wp[EPDE_MAX_LAYERS + 1];      // padded copy of W_l: [n_l][w_{l-1}], 16-byte aligned
+  int64_t size;
+};
 inline NetParams net_params(const GenericPlan& P, const float* params, int net) {
   NetParams R; int64_t per = 0;
   for (int l = 1; l <= P.L; l++) per += (int64_t)P.n[l] * P.n[l - 1] + P.n[l];
-  int64_t o = per * net;
+  int64_t o = per * net, op = P.wp_net * net;
   for (int l = 1; l <= P.L; l++) {
     R.off[l] = o; R.W[l] = params + o; o += (int64_t)P.n[l] * P.n[l - 1]; R.b[l] = params + o; o += P.n[l];
+    R.Wp[l] = P.wp ? P.wp + op : nullptr; op += ((int64_t)P.n[l] * P.w[l - 1] + 3) / 4 * 4;
   }
   R.size = per;
   return R;
+}
+inline void generic_pad_weights(const epde_desc* D, const GenericPlan& P, const float* params, cudaStream_t st) {
+  for (int net = 0; net < D->k; net++) {
+    const NetParams np = net_params(P, params, net);
+    for (int l = 1; l <= P.L; l++)
+      g_pad_weights<<<g_blocks((int64_t)P.n[l] * P.w[l - 1]), 256, 0, st>>>(P.n[l], P.n[l - 1], P.w[l - 1], np.W[l],
+                                                                            const_cast<float*>(np.Wp[l]));
+  }
 }
 
 // forward + input-Jacobian chain of one net on the current chunk (fills Z, A, G, U, U0)
 inline void generic_fwd_jac(const epde_desc* D, const GenericPlan& P, const NetParams& np, int Bc, bool jac,
                             cudaStream_t st) {
   const int L = P.L;
-  const float* Ain = P.Xc; int lda = D->d_pad;
-  for (int l = 1; l <= L; l++) {
-    gemm<false, true>(st, Bc, P.n[l], P.n[l - 1], Ain, lda, np.W[l], P.n[l - 1], P.Z[l], P.n[l], np.b[l], nullptr);
+  const TcCtx tc{P.cpart, P.cpart_floats};
+  const float* Ain = P.Xc;
+  for (int l = 1; l <= L; l++) {           // z_l = W_l a_{l-1} + b_l  (layer 1: K = d_pad, zero-padded columns)
+    gemm<false, true>(st, tc, Bc, P.n[l], P.w[l - 1], Ain, P.w[l - 1], np.Wp[l], P.w[l - 1], P.Z[l], P.n[l], np.b[l],
+                      nullptr);
     if (l < L) {
       g_act<<<g_blocks((int64_t)Bc * P.n[l]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l], P.Z[l], P.A[l]);
-      Ain = P.A[l]; lda = P.n[l];
+      Ain = P.A[l];
     }
   }
   if (!jac) return;
   g_fill<<<g_blocks(Bc), 256, 0, st>>>(Bc, 1.0f, P.G[L]);                       // g_L = 1
   for (int l = L; l >= 1; l--) {
     float* Uout = (l == 1) ? P.U0 : P.U[l - 1];                                   // u_{l-1} = W_l^T g_l
-    gemm<false, false>(st, Bc, P.n[l - 1], P.n[l], P.G[l], P.n[l], np.W[l], P.n[l - 1], Uout, P.n[l - 1], nullptr,
+    gemm<false, false>(st, tc, Bc, P.w[l - 1], P.n[l], P.G[l], P.n[l], np.Wp[l], P.w[l - 1], Uout, P.w[l - 1], nullptr,
                        nullptr);
     if (l > 1)
       g_jacmul<<<g_blocks((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l - 1], P.Z[l - 1],
@@ -311,13 +384,14 @@ inline void generic_fwd_jac(const epde_desc* D, const GenericPlan& P, const NetP
 inline int generic_partial(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                            const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
   GenericPlan P = generic_plan(D, B, ws);
+  generic_pad_weights(D, P, params, st);
   for (int64_t b0 = 0; b0 < B; b0 += P.Bc) {
     const int Bc = (int)((B - b0 < P.Bc) ? B - b0 : P.Bc);
     g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P.Xc);
     for (int net = 0; net < D->k; net++) {
       const NetParams np = net_params(P, params, net);
       generic_fwd_jac(D, P, np, Bc, true, st);
-      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, P.U0, diag, P.Z[P.L], b0, D->k, net, P.ybuf, P.ebuf);
+      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, P.Z[P.L], b0, D->k, net, P.ybuf, P.ebuf);
     }
   }
   int nb = (int)((B + 255) / 256); if (nb > 256) nb = 256;
@@ -332,9 +406,11 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
                           const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
   GenericPlan P = generic_plan(D, B, ws);
   const int L = P.L, act = D->act_id;
+  const TcCtx tc{P.cpart, P.cpart_floats};
   k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, P.coef);
   int64_t per = 0; for (int l = 1; l <= L; l++) per += (int64_t)P.n[l] * P.n[l - 1] + P.n[l];
   g_zero_d<<<g_blocks(per * D->k), 256, 0, st>>>(per * D->k, P.gacc);
+  generic_pad_weights(D, P, params, st);
   for (int64_t b0 = 0; b0 < B; b0 += P.Bc) {
     const int Bc = (int)((B - b0 < P.Bc) ? B - b0 : P.Bc);
     g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P.Xc);
@@ -343,14 +419,14 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
       const NetParams np = net_params(P, params, net);
       generic_fwd_jac(D, P, np, Bc, true, st);
       // ---- first reverse sweep (energy term), l = 1..L
-      g_seed<<<g_blocks((int64_t)Bc * D->d), 256, 0, st>>>(Bc, D->d, P.U0, diag, w, idx, b0, P.coef, net, P.Ub);
+      g_seed<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, w, idx, b0, P.coef, net, P.Ub);
       for (int l = 1; l <= L; l++) {
         // dW_l += g_l^T ubar_{l-1}
-        gemm<true, false>(st, P.n[l], P.n[l - 1], Bc, P.G[l], P.n[l], P.Ub, P.n[l - 1], nullptr, P.n[l - 1], nullptr,
-                          P.gacc + np.off[l]);
+        gemm<true, false>(st, tc, P.n[l], P.w[l - 1], Bc, P.G[l], P.n[l], P.Ub, P.w[l - 1], nullptr, P.n[l - 1], nullptr,
+                          P.gacc + np.off[l], P.n[l - 1]);
         if (l < L) {
           // gbar_l = W_l ubar_{l-1}
-          gemm<false, true>(st, Bc, P.n[l], P.n[l - 1], P.Ub, P.n[l - 1], np.W[l], P.n[l - 1], P.Gb, P.n[l], nullptr,
+          gemm<false, true>(st, tc, Bc, P.n[l], P.w[l - 1], P.Ub, P.w[l - 1], np.Wp[l], P.w[l - 1], P.Gb, P.n[l], nullptr,
                             nullptr);
           g_esweep<<<g_blocks((int64_t)Bc * P.n[l]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l], P.Z[l], P.U[l], P.Gb,
                                                                    P.Ub, P.Zb[l]);
@@ -360,13 +436,12 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
       g_ybar<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->k, net, w, idx, b0, P.ybuf, P.coef, P.Zb[L]);
       for (int l = L; l >= 1; l--) {
         const float* Aprev = (l == 1) ? P.Xc : P.A[l - 1];
-        const int ldp = (l == 1) ? D->d_pad : P.n[l - 1];
-        gemm<true, false>(st, P.n[l], P.n[l - 1], Bc, P.Zb[l], P.n[l], Aprev, ldp, nullptr, P.n[l - 1], nullptr,
-                          P.gacc + np.off[l]);
-        gemm<true, false>(st, P.n[l], 1, Bc, P.Zb[l], P.n[l], P.ones, 1, nullptr, 1, nullptr,
-                          P.gacc + np.off[l] + (int64_t)P.n[l] * P.n[l - 1]);
+        gemm<true, false>(st, tc, P.n[l], P.w[l - 1], Bc, P.Zb[l], P.n[l], Aprev, P.w[l - 1], nullptr, P.n[l - 1], nullptr,
+                          P.gacc + np.off[l], P.n[l - 1]);
+        g_colsum<<<dim3((P.n[l] + 127) / 128, (Bc + 63) / 64), 128, 0, st>>>(
+            Bc, P.n[l], P.Zb[l], P.gacc + np.off[l] + (int64_t)P.n[l] * P.n[l - 1]);
         if (l > 1) {
-          gemm<false, false>(st, Bc, P.n[l - 1], P.n[l], P.Zb[l], P.n[l], np.W[l], P.n[l - 1], P.T, P.n[l - 1], nullptr,
+          gemm<false, false>(st, tc, Bc, P.n[l - 1], P.n[l], P.Zb[l], P.n[l], np.Wp[l], P.w[l - 1], P.T, P.n[l - 1], nullptr,
                              nullptr);
           g_zsweep<<<g_blocks((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l - 1], P.Z[l - 1], P.T,
                                                                        P.Zb[l - 1]);
@@ -386,15 +461,16 @@ inline int generic_forward(const epde_desc* D, const float* X, const int64_t* id
   while (generic_plan(D, cap * 2, nullptr).total <= ws_bytes && cap * 2 <= 65536) cap *= 2;
   if (generic_plan(D, cap, nullptr).total > ws_bytes) cap = 1;
   (void)P0;
+  const GenericPlan P = generic_plan(D, cap, ws);               // one layout for every slab
+  generic_pad_weights(D, P, params, st);
   for (int64_t b0 = 0; b0 < B; b0 += cap) {
     const int Bc = (int)((B - b0 < cap) ? B - b0 : cap);
-    GenericPlan P = generic_plan(D, Bc, ws);
     g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P.Xc);
     for (int net = 0; net < D->k; net++) {
       const NetParams np = net_params(P, params, net);
       generic_fwd_jac(D, P, np, Bc, false, st);
       // strided copy of the output column: ybuf/ebuf helper reused with a dummy energy buffer
-      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, 0, P.U0, nullptr, P.Z[P.L], 0, D->k, net, y + b0 * D->k, P.ebuf);
+      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, 0, D->d_pad, P.U0, nullptr, P.Z[P.L], 0, D->k, net, y + b0 * D->k, P.ebuf);
     }
   }
   return (int)cudaGetLastError();
