@@ -234,6 +234,74 @@ def test_full_size_properties():
     _check(cs, _oracle(cs), rs)
 
 
+def test_full_size_k6_shard_properties():
+    """BASELINE config 4 shape: 50-D, k = 6, one GPU's shard of 2^21 samples.  Size-independent checks:
+    two half-shards combined through partial/finish equal the single call; subsample vs oracle."""
+    from eigenpde_nn_b200 import _lib
+    from eigenpde_nn_b200.engine import StepEngine
+    rng = np.random.default_rng(2)
+    K, B, d, k = 1 << 21, 1 << 21, 50, 6
+    c = _rand_case(19, d, k, [20, 20, 20], 4, 4)
+    X = (0.5 * rng.standard_normal((K, d))).astype(np.float32)
+    w = np.exp(0.3 * rng.standard_normal(K)).astype(np.float32)
+    eng = StepEngine(X, w, c["arch"], k, "Tanh", np.ones(d), 1.0, c["eig_w"])
+    flat = _flat(c["params"])
+    idx = torch.from_numpy(rng.integers(0, K, B)).cuda()
+    out, grad = eng.step_device(idx, B, flat, 20.0)
+    full_out, full_grad = out.clone(), grad.clone()
+    L = eng.lib
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    halves = [idx[: B // 2].contiguous(), idx[B // 2:].contiguous()]
+    sums = torch.zeros(eng.n_sums, dtype=torch.float64, device="cuda")
+    part = torch.zeros_like(sums)
+    ws = eng._workspace(B)
+    args = lambda sh: (C.byref(eng.desc), eng.X.data_ptr(), eng.w.data_ptr(), sh.data_ptr(), sh.numel(),
+                       flat.data_ptr(), eng.diag.data_ptr())
+    for sh in halves:
+        _lib.check(L.epde_step_partial(*args(sh), ws.data_ptr(), ws.numel(), part.data_ptr(), st), "partial")
+        sums += part
+    g2 = torch.zeros_like(full_grad); g1 = torch.zeros_like(full_grad)
+    o2 = torch.zeros_like(full_out)
+    eigw = (C.c_double * k)(*eng.eig_w)
+    for sh in halves:
+        # finish re-uses the workspace of the matching partial: run partial again for this half first
+        _lib.check(L.epde_step_partial(*args(sh), ws.data_ptr(), ws.numel(), part.data_ptr(), st), "partial")
+        _lib.check(L.epde_step_finish(*args(sh), eng.beta, 20.0, eigw, sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      o2.data_ptr(), g1.data_ptr(), st), "finish")
+        g2 += g1
+    torch.cuda.synchronize()
+    assert abs(float(o2[0]) - float(full_out[0])) <= 1e-9 * abs(float(full_out[0]))
+    assert torch.equal(o2[4 + k:4 + 2 * k], full_out[4 + k:4 + 2 * k])           # cvec
+    assert (g2 - full_grad).norm() / full_grad.norm() < 2e-6
+    sub = idx[:4096].cpu().numpy()
+    rs = eng.step(sub, flat, 20.0)
+    cs = dict(c); cs.update(X=X.astype(np.float64), w=w.astype(np.float64), idx=sub)
+    _check(cs, _oracle(cs), rs)
+
+
+def test_cabi_rejects_bad_arguments_on_device():
+    """Error behaviour of the compute entry points: integer codes, never a crash."""
+    from eigenpde_nn_b200 import _lib
+    c = _rand_case(3, 50, 3, [20, 20, 20], 500, 200)
+    eng = _engine(c)
+    flat = _flat(c["params"])
+    L = eng.lib
+    idx = torch.from_numpy(c["idx"]).cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ws = eng._workspace(200)
+    eigw = (C.c_double * 3)(*eng.eig_w)
+    base = (C.byref(eng.desc), eng.X.data_ptr(), eng.w.data_ptr(), idx.data_ptr(), 200, flat.data_ptr(),
+            eng.diag.data_ptr(), 1.0, 20.0, eigw)
+    tail = (eng.out.data_ptr(), eng.grad.data_ptr(), st)
+    assert L.epde_step(*base, ws.data_ptr(), 1024, *tail) == -4                   # workspace too small
+    assert L.epde_step(*base, ws.data_ptr() + 16, ws.numel() - 16, *tail) == -5   # misaligned workspace
+    assert L.epde_step(C.byref(eng.desc), eng.X.data_ptr() + 4, *base[2:], ws.data_ptr(), ws.numel(), *tail) == -5
+    assert L.epde_step(*base[:4], 0, *base[5:], ws.data_ptr(), ws.numel(), *tail) == -6       # B = 0
+    assert L.epde_step(*base[:9], None, ws.data_ptr(), ws.numel(), *tail) == -1               # eig_w NULL
+    assert L.epde_step(*base, ws.data_ptr(), ws.numel(), *tail) == 0
+    torch.cuda.synchronize()
+
+
 def test_forward_only_vs_oracle():
     c = _rand_case(4, 50, 3, [20, 20, 20], 3000, 1001)
     eng = _engine(c)
