@@ -352,6 +352,36 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// averaged_model.nets[i] += model.nets[cvec[i]]  (record_model_parameters, src/pytorch_eigen_solver.py:114-118)
+__global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p, const double* __restrict__ out,
+                          int k, int64_t per) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per * k) return;
+  const int i = (int)(e / per);
+  const int src = (int)out[EPDE_OUT_CVEC(k) + i];
+  avg[e] += (double)p[(int64_t)src * per + (e - (int64_t)i * per)];
+}
+// running sums of the sorted eigenvalue estimates and their squares (:280-282)
+__global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict__ out, int k) {
+  const int i = threadIdx.x;
+  if (i < k) { const double e = out[EPDE_OUT_EIG(k) + i]; stats[i] += e; stats[k + i] += e * e; }
+}
+
+int epde_average_accumulate(const epde_desc* D, double* avg, const float* params, const double* out, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!avg || !params || !out) return EPDE_ERR_NULL;
+  const int64_t n = param_count(D), per = n / D->k;
+  k_avg_acc<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(avg, params, out, D->k, per);
+  return (int)cudaGetLastError();
+}
+
+int epde_eig_stats_accumulate(const epde_desc* D, double* stats, const double* out, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!stats || !out) return EPDE_ERR_NULL;
+  k_eig_stats<<<1, 32, 0, (cudaStream_t)stream>>>(stats, out, D->k);
+  return (int)cudaGetLastError();
+}
+
 int epde_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, int64_t step, void* stream) {
   if (!p || !g || !m || !v) return EPDE_ERR_NULL;
   if (n < 1 || step < 1) return EPDE_ERR_ARG;

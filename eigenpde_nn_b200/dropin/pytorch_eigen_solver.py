@@ -137,6 +137,8 @@ class eigen_solver():
                 np.asarray(res["penalty"]))
 
     def train(self):
+        if os.environ.get("EPDE_DEVICE_LOOP") == "1":
+            return self.train_device_resident()
         stage_index = 0
         log_f = open('./data/%s' % self.log_filename, 'w')
         for i in range(self.train_max_step):
@@ -177,6 +179,66 @@ class eigen_solver():
                 torch.save(self.averaged_model, './data/%s_stage%d_averaged.pt' % (self.eig_file_name_prefix, stage_index))
 
             if i % self.print_every_step == 0:
+                print('\ni=%d, stage %d' % (i, stage_index))
+                print('   loss= %.4e' % (loss))
+                print('   eigenvalues= ', eig_vals)
+                print('   constraints= %.4e' % (penalty), flush=True)
+                print('   runtime: %.2f Sec' % (time.process_time() - self.start_time))
+                log_f.write('%d ' % i)
+                row = [loss, non_penalty_loss, penalty] + list(eig_vals)
+                np.savetxt(log_f, np.asarray(row, dtype=np.float64).reshape(1, -1), fmt="%.6f")
+                log_f.flush()
+        log_f.close()
+
+    def train_device_resident(self):
+        """Opt-in (EPDE_DEVICE_LOOP=1) version of `train` (:250-318) with the same stages, files and log
+        lines, whose loop body stays on the GPU: fp32 Adam (epde_adam_step), cvec-ordered averaging
+        (epde_average_accumulate) and the eigenvalue running sums (epde_eig_stats_accumulate).  The host
+        draws the minibatch indices (same MT19937 stream) and only synchronises every print_every_step
+        and at stage ends.  Numerics: parameters and Adam moments are fp32 here (fp64 in the default
+        loop), so trajectories agree with the reference to fp32 round-off, not to 1e-5 after many steps."""
+        from eigenpde_nn_b200.engine import DeviceTrainer
+        trainer = DeviceTrainer(self.engine, self.model)
+        stage_index = 0
+        log_f = open('./data/%s' % self.log_filename, 'w')
+        for i in range(self.train_max_step):
+            if i == self.stage_list[stage_index]:
+                bsz = self.batch_size_list[stage_index]
+                lr = self.learning_rate_list[stage_index]
+                alpha_val = self.alpha_list[stage_index]
+                trainer.start_stage()
+                print('\n[Info] Start %dth training stage from step %d\n\t batch size=%d, lr=%.4f, alpha=%.2f\n' % (
+                    stage_index + 1, i, bsz, lr, alpha_val))
+                stage_index += 1
+
+            idx = self.dataset.draw_indices(bsz)
+            trainer.step(idx, lr, alpha_val)
+
+            if i + 1 == self.stage_list[stage_index] or i + 1 == self.train_max_step:
+                tot_step_in_stage = i + 1 - self.stage_list[stage_index - 1]
+                eig_vals, cvec, loss, non_penalty_loss, penalty = trainer.read_scalars()
+                stats = trainer.stats.cpu().numpy()
+                mean_eig_vals = stats[:self.k] / tot_step_in_stage
+                var_eig_vals = stats[self.k:] / tot_step_in_stage - mean_eig_vals ** 2
+                print('\nStage %d, Step %d to %d (total %d steps):' % (
+                    stage_index, self.stage_list[stage_index - 1], i, tot_step_in_stage))
+                for ii in range(self.k):
+                    print('  %dth eig:  mean=%.4f, var=%.4f' % (ii + 1, mean_eig_vals[ii],
+                                                               math.sqrt(max(var_eig_vals[ii], 0.0))))
+                trainer.download(self.model, "params")
+                self.zero_model_parameters(self.model_bak)
+                self.copy_model_to_bak(cvec)
+                self.update_mean_and_var_of_model(self.model_bak)
+                torch.save(self.model_bak, './data/%s_stage%d.pt' % (self.eig_file_name_prefix, stage_index))
+                self.zero_model_parameters(self.averaged_model)
+                trainer.download(self.averaged_model, "avg")
+                for param in self.averaged_model.parameters():
+                    param /= tot_step_in_stage
+                self.update_mean_and_var_of_model(self.averaged_model)
+                torch.save(self.averaged_model, './data/%s_stage%d_averaged.pt' % (self.eig_file_name_prefix, stage_index))
+
+            if i % self.print_every_step == 0:
+                eig_vals, cvec, loss, non_penalty_loss, penalty = trainer.read_scalars()
                 print('\ni=%d, stage %d' % (i, stage_index))
                 print('   loss= %.4e' % (loss))
                 print('   eigenvalues= ', eig_vals)

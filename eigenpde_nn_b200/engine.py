@@ -175,3 +175,62 @@ class EigenLossFn(torch.autograd.Function):
             outs.append(g[off:off + n].view(shp))
             off += n
         return (None, None, None) + tuple(outs)
+
+
+class DeviceTrainer:
+    """Device-resident version of the per-step loop body of `eigen_solver.train`
+    (src/pytorch_eigen_solver.py:277-284): loss+gradient step, Adam (torch.optim.Adam defaults, fp32),
+    model averaging in cvec order and the eigenvalue running sums all stay on the GPU; the host only
+    draws the minibatch indices and enqueues.  Nothing is synchronised until `read_scalars()` /
+    `download()` is called (every print_every_step / at a stage end)."""
+
+    def __init__(self, engine: StepEngine, model):
+        self.e = engine
+        dev = engine.device
+        self.p = engine.flat_params(model)
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.avg = torch.zeros(engine.n_params, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(2 * engine.k, dtype=torch.float64, device=dev)
+        self.t = 0                       # Adam step count (never reset: the reference keeps one optimiser, :379)
+        self.steps_in_stage = 0
+        self._idx_dev = None
+
+    def start_stage(self):
+        self.avg.zero_()
+        self.stats.zero_()
+        self.steps_in_stage = 0
+
+    def step(self, idx, lr, alpha):
+        e = self.e
+        B = len(idx)
+        if self._idx_dev is None or self._idx_dev.numel() != B:
+            self._idx_dev = torch.empty(B, dtype=torch.int64, device=e.device)
+        self._idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)))
+        out, grad = e.step_device(self._idx_dev, B, self.p, float(alpha))
+        st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
+        # the reference averages the parameters AFTER the optimiser step of the same iteration (:277, :284)
+        self.t += 1
+        _lib.check(e.lib.epde_adam_step(_ptr(self.p), _ptr(grad), _ptr(self.m), _ptr(self.v), C.c_int64(e.n_params),
+                                        C.c_double(lr), C.c_int64(self.t), st), "epde_adam_step")
+        _lib.check(e.lib.epde_average_accumulate(C.byref(e.desc), _ptr(self.avg), _ptr(self.p), _ptr(out), st),
+                   "epde_average_accumulate")
+        _lib.check(e.lib.epde_eig_stats_accumulate(C.byref(e.desc), _ptr(self.stats), _ptr(out), st),
+                   "epde_eig_stats_accumulate")
+        self.steps_in_stage += 1
+
+    def read_scalars(self):
+        """Host copy of the last step's (eig_vals, cvec, loss, non_penalty, penalty); synchronises."""
+        h = self.e.out.cpu().numpy()
+        k = self.e.k
+        return h[4:4 + k].copy(), h[4 + k:4 + 2 * k].astype(np.int64), h[0], h[1], h[2]
+
+    def download(self, model, source="params"):
+        """Copy the device parameters (or the accumulated average) into a host MyNet."""
+        flat = (self.p.double() if source == "params" else self.avg).cpu()
+        off = 0
+        with torch.no_grad():
+            for prm in model.parameters():
+                n = prm.numel()
+                prm.copy_(flat[off:off + n].view_as(prm).to(prm.dtype))
+                off += n

@@ -162,6 +162,17 @@ int epde_mt_seed(const uint32_t* h_key, int32_t key_len, uint32_t* h_mt, int32_t
 int epde_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
                    int64_t n, double lr, int64_t step, void* stream);
 
+/*
+ * Device-side pieces of the per-step bookkeeping of `train` (src/pytorch_eigen_solver.py:280-284), so a
+ * training loop can run without a host round trip per step:
+ *   epde_average_accumulate: d_avg[net i] += d_params[net cvec[i]]   (record_model_parameters, :114-118;
+ *                            cvec is read from d_out_scalars on the device), d_avg is fp64 [param_count]
+ *   epde_eig_stats_accumulate: d_stats[0..k) += eig, d_stats[k..2k) += eig^2   (:280-282)
+ */
+int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d_params,
+                            const double* d_out_scalars, void* stream);
+int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

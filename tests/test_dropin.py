@@ -107,9 +107,16 @@ def test_constructor_matches_reference_contract(dropin, tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch):
+@pytest.mark.parametrize("device_loop", [False, True])
+def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch, device_loop):
     """Same seed, same data file: 10 Adam steps over two stages.  The reference log is fp64 CPU;
-    ours is the fp32 CUDA step + the same fp64 host Adam, so the trajectories agree to ~1e-5."""
+    ours is the fp32 CUDA step + the same fp64 host Adam, so the trajectories agree to ~1e-5.
+    device_loop=True runs the opt-in device-resident loop (fp32 Adam, averaging and eigenvalue
+    statistics on the GPU, EPDE_DEVICE_LOOP=1) against the same reference log and checkpoints."""
+    if device_loop:
+        monkeypatch.setenv("EPDE_DEVICE_LOOP", "1")
+    else:
+        monkeypatch.delenv("EPDE_DEVICE_LOOP", raising=False)
     z = np.load(os.path.join(GOLDEN, "dropin_run.npz"))
     (tmp_path / "data").mkdir()
     with open(tmp_path / "data" / "states.txt", "w") as fh:

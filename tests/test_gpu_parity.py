@@ -347,3 +347,39 @@ def test_fused_adam_matches_torch():
         _lib.check(L.epde_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 5e-3, step,
                                     torch.cuda.current_stream().cuda_stream), "adam")
     assert torch.allclose(p.cpu(), ref_p.detach(), rtol=2e-5, atol=1e-6)
+
+
+def test_device_side_averaging_and_eig_stats():
+    """epde_average_accumulate / epde_eig_stats_accumulate against the host bookkeeping of the reference's
+    `train` (record_model_parameters :114-118, running eigenvalue sums :280-282)."""
+    import ctypes as C
+    from eigenpde_nn_b200 import _lib
+    L = _lib.lib()
+    k, arch = 3, [50, 20, 20, 20, 1]
+    desc = _lib.make_desc(arch, k, "Tanh", 52)
+    n = C.c_int64()
+    _lib.check(L.epde_param_count(C.byref(desc), C.byref(n)), "count")
+    n, per = n.value, n.value // k
+    g = torch.Generator().manual_seed(3)
+    avg = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stats = torch.zeros(2 * k, dtype=torch.float64, device="cuda")
+    want_avg = np.zeros(n)
+    want_stats = np.zeros(2 * k)
+    st = torch.cuda.current_stream().cuda_stream
+    for it in range(4):
+        p = torch.randn(n, generator=g)
+        cvec = torch.randperm(k, generator=g).numpy()
+        eig = torch.rand(k, generator=g, dtype=torch.float64).numpy()
+        out = np.zeros(4 + 4 * k)
+        out[4:4 + k] = eig
+        out[4 + k:4 + 2 * k] = cvec
+        pd, od = p.cuda(), torch.from_numpy(out).cuda()
+        _lib.check(L.epde_average_accumulate(C.byref(desc), avg.data_ptr(), pd.data_ptr(), od.data_ptr(), st), "avg")
+        _lib.check(L.epde_eig_stats_accumulate(C.byref(desc), stats.data_ptr(), od.data_ptr(), st), "stats")
+        pn = p.numpy().astype(np.float64)
+        for i in range(k):
+            want_avg[i * per:(i + 1) * per] += pn[cvec[i] * per:(cvec[i] + 1) * per]
+        want_stats[:k] += eig
+        want_stats[k:] += eig ** 2
+    assert np.array_equal(avg.cpu().numpy(), want_avg)          # fp64 sums of fp32 values: exact
+    assert np.allclose(stats.cpu().numpy(), want_stats, rtol=1e-15)
