@@ -20,7 +20,7 @@ FLAG_SORT = 1
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
            "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
-           "epde_eig_stats_accumulate"]
+           "epde_eig_stats_accumulate", "epde_set_fused_impl"]
 
 
 class EpdeDesc(C.Structure):
@@ -60,6 +60,7 @@ def lib():
         L.epde_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, i64, vp]
         L.epde_average_accumulate.argtypes = [dp, vp, vp, vp, vp]
         L.epde_eig_stats_accumulate.argtypes = [dp, vp, vp, vp]
+        L.epde_set_fused_impl.argtypes = [C.c_int]
         for name in EXPORTS:
             if name != "epde_error_string":
                 getattr(L, name).restype = C.c_int

@@ -20,6 +20,18 @@ def _sources():
     return srcs, deps
 
 
+def _deps_of(src, seen=None):
+    """Transitive closure of the quoted #include files of one source."""
+    import re
+    seen = set() if seen is None else seen
+    if src in seen or not os.path.exists(src):
+        return seen
+    seen.add(src)
+    for m in re.finditer(r'^\s*#include\s+"([^"]+)"', open(src).read(), re.M):
+        _deps_of(os.path.normpath(os.path.join(os.path.dirname(src), m.group(1))), seen)
+    return seen
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -28,17 +40,41 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    """Compile every csrc/*.cu to an object (in parallel, only the stale ones) and link the shared library."""
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs, _ = _sources()
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    srcs, deps = _sources()
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    tag = os.path.join(objdir, "flags.txt")
+    same_flags = os.path.exists(tag) and open(tag).read() == " ".join(flags)
+    procs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if (not force and same_flags and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(p) for p in _deps_of(src))):
+            continue
+        procs.append((src, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            failed = True
+            sys.stderr.write(out)
+        elif verbose:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc failed building %s" % LIB)
+    open(tag, "w").write(" ".join(flags))
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc failed linking %s" % LIB)
     return LIB
 
 

@@ -8,6 +8,7 @@
 #include "epde_coef.cuh"
 #include "epde_fused.cuh"
 #include "epde_generic.cuh"
+#include "epde_tc_api.h"
 
 using namespace epde;
 
@@ -15,6 +16,7 @@ namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
 constexpr int kFusedH = 20;
+int g_fused_impl = 0;                  // 0: FFMA2 kernels (epde_fused.cuh)   1: tcgen05 kernels (epde_tc_fused.cuh)
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
@@ -51,7 +53,8 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 
 // ---- workspace ------------------------------------------------------------------------------
 struct FusedWs {
-  float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; size_t total;
+  float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
+  size_t total;
 };
 FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   char* p = (char*)base; size_t off = 0; FusedWs W;
@@ -64,6 +67,8 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   const size_t ntl = (size_t)((B + GT - 1) / GT);
   W.xt = (float*)take(ntl * D->d_pad * GT * 4);
   W.wt = (float*)take(ntl * GT * 4);
+  W.pwt = (float*)take((size_t)D->k * tc::pack_floats(D->d) * 4);
+  W.part2 = (double*)take((size_t)kMaxCtas * 32 * 8);
   W.total = off;
   return W;
 }
@@ -98,11 +103,11 @@ cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt
 
 // gather + transpose the minibatch rows into the tile-major copy (workspace xt / wt)
 cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
-                          float* xt, float* wt, cudaStream_t st) {
+                          float* xt, float* wt, cudaStream_t st, int tile128 = 0) {
   const size_t smem = (size_t)GT * (D->d_pad + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_gather<0><<<(unsigned)((B + GT - 1) / GT), 256, smem, st>>>(X, w, idx, B, D->d_pad, xt, wt);
+  k_gather<0><<<(unsigned)((B + GT - 1) / GT), 256, smem, st>>>(X, w, idx, B, D->d_pad, xt, wt, tile128);
   return cudaGetLastError();
 }
 
@@ -111,8 +116,10 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
-  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st);
+  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, g_fused_impl == 1);
   if (e != cudaSuccess) return (int)e;
+  if (g_fused_impl == 1)
+    return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums, st);
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
@@ -139,7 +146,15 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
                  const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
-  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
+  k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
+  if (g_fused_impl == 1) {
+    int gx = 0;
+    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx, st);
+    if (rc) return rc;
+    const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
+    k_fin2<kFusedH><<<D->k, 512, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+    return (int)cudaGetLastError();
+  }
   const int64_t ntiles = (B + P2_T - 1) / P2_T;
   int gx = nsm / D->k; if (gx < 1) gx = 1;
   if (gx > ntiles) gx = (int)ntiles;
@@ -365,6 +380,12 @@ __global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p,
 __global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict__ out, int k) {
   const int i = threadIdx.x;
   if (i < k) { const double e = out[EPDE_OUT_EIG(k) + i]; stats[i] += e; stats[k + i] += e * e; }
+}
+
+int epde_set_fused_impl(int impl) {
+  if (impl != 0 && impl != 1) return EPDE_ERR_ARG;
+  g_fused_impl = impl;
+  return EPDE_OK;
 }
 
 int epde_average_accumulate(const epde_desc* D, double* avg, const float* params, const double* out, void* stream) {

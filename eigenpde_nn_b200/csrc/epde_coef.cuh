@@ -17,6 +17,7 @@ struct EigW { double v[EPDE_MAX_K]; };
 // Everything that depends only on the batch-global sums: eig_vals, cvec, losses
 // (src/pytorch_eigen_solver.py:215-229, 177-189) and the per-sample seed coefficients of the
 // reverse pass (SURVEY.md 8(a) closed form).  One thread; k <= 8.
+template <int DUMMY = 0>
 __global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
                        double* __restrict__ out, Coef* __restrict__ coef) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;

@@ -109,7 +109,7 @@ constexpr int GT = 256;                       // samples per tile (= P2_T)
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256)
 k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
-         int d_pad, float* __restrict__ xt, float* __restrict__ wt) {
+         int d_pad, float* __restrict__ xt, float* __restrict__ wt, int tile128) {
   extern __shared__ float4 smem4[];
   float* ts = reinterpret_cast<float*>(smem4);           // [256][d_pad + 1]
   __shared__ int64_t srow[GT];
@@ -129,6 +129,11 @@ k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t
     dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
   }
   __syncthreads();
+  if (tile128) {      // tensor-core family: 128-sample tiles, xt[tile128][j][128] (one contiguous block per tile)
+    float* out = xt + (size_t)(tile * 2 + (t >> 7)) * d_pad * 128 + (t & 127);
+    for (int j = 0; j < d_pad; j++) out[(size_t)j * 128] = ts[t * ld + j];
+    return;
+  }
   float* out = xt + (size_t)tile * d_pad * GT;
   for (int j = 0; j < d_pad; j++) out[(size_t)j * GT + t] = ts[t * ld + j];
 }

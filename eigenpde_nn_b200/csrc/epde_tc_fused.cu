@@ -1,0 +1,60 @@
+// Launchers of the tensor-core fused family (separate translation unit: these kernels are large).
+#include "epde_tc_api.h"
+#include "epde_tc_fused.cuh"
+#include "epde_tc_pass2.cuh"
+
+#ifdef EPDE_PHASE_TIMING
+extern "C" int epde_debug_tc_cycles(unsigned long long* h16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(h16, epde::tc::g_tc_cycles, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(epde::tc::g_tc_cycles, z, sizeof(z)); }
+  return (int)e;
+}
+#endif
+
+namespace epde {
+namespace tc {
+
+size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
+
+int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
+            const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, cudaStream_t st) {
+  const TcPack TL(d);
+  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt);
+  const int64_t nt128 = (B + 127) / 128;
+  int gx = nsm / k; if (gx < 1) gx = 1;
+  if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
+  const size_t smem = ((size_t)TL.total() + (size_t)TG * TXR * 128) * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(k_pass1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_pass1_tc<<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);
+  e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
+  int g2 = (int)((B + 255) / 256); if (g2 > nsm) g2 = nsm;
+  switch (k) {
+    case 1: k_sums_y<1><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    case 2: k_sums_y<2><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    case 3: k_sums_y<3><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    case 4: k_sums_y<4><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    case 5: k_sums_y<5><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    default: k_sums_y<6><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+  }
+  k_reduce_tc<<<1, 64, 0, st>>>(part, gx, part2, g2, k, sums);
+  return (int)cudaGetLastError();
+}
+
+int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
+           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st) {
+  const TcPack TL(d);
+  const int64_t nt128 = (B + 127) / 128;
+  int gx = nsm / k; if (gx < 1) gx = 1;
+  if ((int64_t)gx * P2G > nt128) gx = (int)((nt128 + P2G - 1) / P2G);
+  const int gn = GradLayout<TH>(d_pad).total();
+  const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)((gn + 7) & ~7) * 4 + 128;
+  cudaError_t e = cudaFuncSetAttribute(k_pass2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  k_pass2_tc<<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg);
+  *gx_out = gx;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace epde

@@ -1,0 +1,396 @@
+// k_pass2_tc: phase 2 of the fused step on the tensor cores (see epde_tc_fused.cuh for the conventions).
+//
+// Per 128-sample tile and net, thread = sample:
+//   mat-vec chain (TS-form MMAs, A in TMEM):  x -> a1 -> a2 -> a3 | g3 -> u2 | g2 -> u1 | g1 -> K g1 |
+//       ubar1 -> gbar2 | ubar2 -> gbar3 | zbar3 -> W3^T zbar3 | zbar2 -> W2^T zbar2 -> zbar1
+//   weight gradients = contractions over the SAMPLES:  G[p][q] = sum_n P[n][p] Q[n][q]  (SS-form MMAs, M = 64):
+//       the P / Q vectors of a "round" are written by their threads into a shared staging buffer as K-major
+//       [feature][sample] images (hi / lo), several vectors stacked along M and along N:
+//         round 1:  M = [g2 | g3 | ebar g1]        N = [ubar1 | ubar2 | g1]      -> dW2 (g part), dW3 (g part), Gamma
+//         round 2:  M = [zbar2 | zbar3 | s4 | ybar] N = [a1 | 1 | a2 | 1]         -> dW2, db2, dW3, db3, dw4, db4
+//         round 3:  M = [zbar1]                     N = [x | 1]                   -> dW1 (z part), db1
+//   The two groups of a CTA share ONE staging buffer: rounds are serialised by a ticket, round T commits to
+//   ring[T % 4] and the holder of ticket T waits for round T-1 before it touches the buffer.  The accumulators of a
+//   round live in TMEM only for that round (the fp32 accumulator truncates, so nothing is accumulated across
+//   tiles there): the next holder of the same round type first adds them (round-to-nearest) into the per-CTA
+//   shared-memory gradient image.
+#pragma once
+#include "epde_tc_fused.cuh"
+
+namespace epde {
+namespace tc {
+
+constexpr int P2G = 2;                          // groups per CTA (long-lived per-sample state stays in registers)
+constexpr int P2THREADS = 128 * P2G;
+constexpr uint32_t SG_LBO = 144;                // bytes between 4-sample chunks of a staging row group (conflict-free STS.32)
+constexpr uint32_t SG_SBO = 32 * SG_LBO;        // bytes between 8-row groups (128 samples)
+constexpr int SG_ROWS = 64;                     // rows per image
+constexpr uint32_t SG_IMG = (SG_ROWS / 8) * SG_SBO;   // one image (hi or lo) = 36864 B
+// staging buffer: [M hi][M lo][N hi][N lo]
+constexpr uint32_t SG_BYTES = 4 * SG_IMG;
+
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+// write value v of staging row r (this thread's sample column) into the hi and lo images starting at img
+__device__ __forceinline__ void stage_val(uint32_t img_hi, int r, float v) {
+  float hi, lo; split_tf32(v, hi, lo);
+  const uint32_t o = (uint32_t)(r >> 3) * SG_SBO + (uint32_t)(r & 7) * 16u;
+  sts32(img_hi + o, hi); sts32(img_hi + SG_IMG + o, lo);
+}
+
+// one gradient round: D[64 x N] = sum over 128 samples, 3xTF32, small terms first; fresh accumulator
+template <int N>
+__device__ __forceinline__ void issue_round(uint32_t d_t, uint32_t sg_base) {
+  const uint32_t idesc = idesc_tf32(64, N);
+  const uint64_t mh = kdesc(sg_base, SG_LBO, SG_SBO), ml = kdesc(sg_base + SG_IMG, SG_LBO, SG_SBO);
+  const uint64_t nh = kdesc(sg_base + 2 * SG_IMG, SG_LBO, SG_SBO), nl = kdesc(sg_base + 3 * SG_IMG, SG_LBO, SG_SBO);
+#pragma unroll
+  for (int ks = 0; ks < 16; ks++) {               // 8 samples per MMA = two 4-sample chunks = 288 B = 18 address units
+    mma_ss(d_t, ml + 18 * ks, nh + 18 * ks, idesc, ks ? 1u : 0u);
+    mma_ss(d_t, mh + 18 * ks, nl + 18 * ks, idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < 16; ks++) mma_ss(d_t, mh + 18 * ks, nh + 18 * ks, idesc, 1u);
+}
+__device__ __forceinline__ void issue_round_rt(int n8, uint32_t d_t, uint32_t sg_base) {
+  switch (n8) {
+    case 1: issue_round<8>(d_t, sg_base); break;
+    case 2: issue_round<16>(d_t, sg_base); break;
+    case 3: issue_round<24>(d_t, sg_base); break;
+    case 4: issue_round<32>(d_t, sg_base); break;
+    case 5: issue_round<40>(d_t, sg_base); break;
+    case 6: issue_round<48>(d_t, sg_base); break;
+    case 7: issue_round<56>(d_t, sg_base); break;
+    default: issue_round<64>(d_t, sg_base); break;
+  }
+}
+
+__global__ void __launch_bounds__(P2THREADS, 1)
+k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad, int K,
+           const float* __restrict__ pwt, const float* __restrict__ ybuf, const Coef* __restrict__ coef,
+           float* __restrict__ pg) {
+  constexpr int H = TH;
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  const TcPack L(d);
+  const GradLayout<H> G(d_pad);
+  const int gn = G.total();
+  unsigned char* sg = tsm;                                          // staging buffer (SG_BYTES)
+  float* sw = reinterpret_cast<float*>(tsm + SG_BYTES);             // packed weights
+  float* acc = sw + L.total();                                      // per-CTA gradient image (GradLayout)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(acc + ((gn + 7) & ~7));   // [P2G] mat-vec, [4] round ring
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + P2G + 4);     // [0] tmem base, [1] ticket, [2..] ticket of group
+  const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, wq = warp & 3, lane = tid & 31, net = blockIdx.y;
+  const int sn = tid & 127;                                         // sample within the tile = TMEM lane
+  {
+    const float* src = pwt + (size_t)net * L.total();
+    for (int i = tid; i < L.total(); i += P2THREADS) sw[i] = src[i];
+    for (int i = tid; i < gn; i += P2THREADS) acc[i] = 0.f;
+    for (uint32_t i = tid; i < SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
+  }
+  if (tid == 0) { for (int i = 0; i < P2G + 4; i++) mbar_init(bars + i, 1); slot[1] = 0; }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before(); __syncthreads(); fence_after();
+  const uint32_t tm = slot[0];
+  const int K1 = L.K1(), ks1 = L.ks1;
+  const int KA = K1 > TKH ? K1 : TKH;
+  const uint32_t gc = (uint32_t)g * (2 * KA + TN);
+  const uint32_t tl = tm + ((uint32_t)(wq * 32) << 16);
+  const uint32_t ahi = gc, alo = gc + KA, dcol = gc + 2 * KA;
+  const uint32_t gbase = (uint32_t)P2G * (2 * KA + TN);             // gradient accumulators: D1 (64), D2 (48), D3 (K1)
+  const uint32_t D1 = gbase, D2 = gbase + 64, D3 = gbase + 112;
+  {  // zero the accumulators once (the first flush of every round type adds them)
+    float zr[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) zr[i] = 0.f;
+    if (g == 0) { for (uint32_t c = 0; c < 112 + (uint32_t)K1; c += 16) tm_st16(tl + gbase + c, zr); wait_st(); }
+  }
+  const uint32_t idesc = idesc_tf32(128, TN);
+  const uint32_t sbase = smem_u32(sw), sgb = smem_u32(sg);
+  const uint64_t dW1h = kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32), dW1l = kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32);
+  uint64_t dMh[5], dMl[5];
+#pragma unroll
+  for (int m = 0; m < 5; m++) {
+    dMh[m] = kdesc(sbase + L.mat(m, 0) * 4, 128, TKH * 32); dMl[m] = kdesc(sbase + L.mat(m, 1) * 4, 128, TKH * 32);
+  }
+  const float b4r = sw[L.b4()];
+  const float ecoef = coef->ecoef[net], cm = coef->cm[net];
+  float cw[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cw[j] = (j < K) ? coef->Cw[net][j] : 0.f;
+  uint64_t* bar = bars + g;
+  uint64_t* ring = bars + P2G;
+  uint32_t ph = 0;
+  // this thread's column inside a staging image
+  const uint32_t tcol = (uint32_t)(sn >> 2) * SG_LBO + (uint32_t)(sn & 3) * 4u;
+  const uint32_t sM = sgb + tcol, sN = sgb + 2 * SG_IMG + tcol;
+  fence_before(); __syncthreads(); fence_after();
+
+  // ---- flush of a round's accumulator (M = 64 layout: row r in lane (r / 16) * 32 + r % 16) into acc ----------
+  auto flush1 = [&]() {       // D1: rows g2 | g3 | ebar g1, cols ubar1 | ubar2 | g1
+    const int r = 16 * wq + lane;
+    float v[16];
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      tm_ld16(tl + D1 + c0, v); wait_ld();
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int c = c0 + i;
+          if (c < 20) { if (r < 20) atomicAdd(acc + G.gW2() + r * H + c, v[i]); }
+          else if (c < 40) { if (r >= 20 && r < 40) atomicAdd(acc + G.gW3() + (r - 20) * H + (c - 20), v[i]); }
+          else if (c < 60) { if (r >= 40 && r < 60) atomicAdd(acc + G.Gam() + (r - 40) * H + (c - 40), v[i]); }
+        }
+      }
+    }
+  };
+  auto flush2 = [&]() {       // D2: rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
+    const int r = 16 * wq + lane;
+    float v[16];
+#pragma unroll
+    for (int c0 = 0; c0 < 48; c0 += 16) {
+      tm_ld16(tl + D2 + c0, v); wait_ld();
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int c = c0 + i;
+          if (c < 20) { if (r < 20) atomicAdd(acc + G.gW2() + r * H + c, v[i]); }
+          else if (c == 20) {
+            if (r < 20) atomicAdd(acc + G.gb2() + r, v[i]);
+            else if (r >= 40 && r < 60) atomicAdd(acc + G.gw4() + (r - 40), v[i]);
+            else if (r == 60) atomicAdd(acc + G.gb4(), v[i]);
+          }
+          else if (c < 41) { if (r >= 20 && r < 40) atomicAdd(acc + G.gW3() + (r - 20) * H + (c - 21), v[i]); }
+          else if (c == 41) { if (r >= 20 && r < 40) atomicAdd(acc + G.gb3() + (r - 20), v[i]); }
+        }
+      }
+    }
+  };
+  auto flush3 = [&]() {       // D3: rows zbar1, cols x | 1
+    const int r = 16 * wq + lane;
+    float v[16];
+#pragma unroll 1
+    for (int c0 = 0; c0 < K1; c0 += 16) {
+      tm_ld16(tl + D3 + c0, v); wait_ld();
+      if (lane < 16 && r < 20) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int c = c0 + i;
+          if (c < d) atomicAdd(acc + G.gW1() + r * d_pad + c, v[i]);
+          else if (c == d) atomicAdd(acc + G.gb1() + r, v[i]);
+        }
+      }
+    }
+  };
+  // take the staging buffer: ticket T, wait for round T-1 (its MMAs have read the buffer and written their D)
+  auto acquire = [&]() -> uint32_t {
+    if (sn == 0) slot[2 + g] = atomicAdd(slot + 1, 1u);
+    group_bar(g);
+    const uint32_t T = slot[2 + g];
+    if (T > 0) mbar_wait(ring + ((T - 1) & 3), ((T - 1) >> 2) & 1);
+    fence_after();
+    return T;
+  };
+#define EPDE_P2_ROUND_ISSUE(T, ISSUE)                                                                  \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                     \
+    fence_before(); group_bar(g);                                                                    \
+    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); }
+
+#define EPDE_P2_ISSUE(ISSUE)                                                                         \
+    fence_before(); group_bar(g);                                                                    \
+    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(bar); } __syncwarp(); }
+#define EPDE_P2_WAIT() mbar_wait(bar, ph); ph ^= 1; fence_after();
+#define EPDE_P2_MV(m) issue_matvec<3>(tm + dcol, tm + ahi, tm + alo, dMh[m], dMl[m], idesc)
+
+  const int64_t nt128 = (B + 127) / 128;
+  const int64_t tstep = (int64_t)gridDim.x * P2G;
+#pragma unroll 1
+  for (int64_t t = (int64_t)blockIdx.x * P2G + g; t < nt128; t += tstep) {
+    const int64_t n = t * 128 + sn;
+    const float* xcol = xt + (size_t)t * d_pad * 128 + sn;
+    const float wn = __ldg(wt + n);
+    float ybar = -cm;
+    if (n < B) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (j < K) ybar = fmaf(cw[j], __ldg(ybuf + n * K + j), ybar);
+    }
+    ybar *= wn;                                     // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
+    const float ebar = wn * ecoef;
+    // ---- S0: x -> A -------------------------------------------------------------------------------
+    {
+      float xv[64];
+#pragma unroll
+      for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (c < ks1) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) split_tf32(xv[8 * c + i], hi[i], lo[i]);
+          tm_st8(tl + ahi + 8 * c, hi); tm_st8(tl + alo + 8 * c, lo);
+        }
+      }
+      wait_st();
+    }
+    EPDE_P2_ISSUE(issue_matvec_rt(ks1, tm + dcol, tm + ahi, tm + alo, dW1h, dW1l, idesc))
+    EPDE_P2_WAIT()
+    float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
+    v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
+    // ---- S1 .. S2: a1, a2 ---------------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+#pragma unroll
+    for (int i = 0; i < H; i++) { a1[i] = tanh1(z[i]); v[i] = a1[i]; }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(0))
+    EPDE_P2_WAIT()
+    tm_ld20(tl + dcol, z);
+#pragma unroll
+    for (int i = 0; i < H; i++) { a2[i] = tanh1(z[i]); v[i] = a2[i]; }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(1))
+    EPDE_P2_WAIT()
+    // ---- S3: a3, g3 -> u2 ---------------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+    v[20] = 0.f;                                      // no bias row from here on
+#pragma unroll
+    for (int i = 0; i < H; i++) { a3[i] = tanh1(z[i]); v[i] = fmaf(-a3[i], a3[i], 1.f) * sw[L.w4() + i]; }   // g3
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(3))
+    EPDE_P2_WAIT()
+    // ---- S4: g2 -> u1 -------------------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+#pragma unroll
+    for (int i = 0; i < H; i++) { g2[i] = fmaf(-a2[i], a2[i], 1.f) * z[i]; v[i] = g2[i]; }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(2))
+    EPDE_P2_WAIT()
+    // ---- S5: g1 -> K g1 -----------------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+#pragma unroll
+    for (int i = 0; i < H; i++) { g1[i] = fmaf(-a1[i], a1[i], 1.f) * z[i]; v[i] = g1[i]; }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(4))
+    EPDE_P2_WAIT()
+    // ---- S6: gbar1 = 2 ebar K g1, ubar1 -> gbar2 = W2 ubar1 --------------------------------------------
+    tm_ld20(tl + dcol, z);
+    float ub1[H];
+    {
+      const float e2 = 2.f * ebar;
+#pragma unroll
+      for (int i = 0; i < H; i++) {
+        const float gb = e2 * z[i];
+        ub1[i] = fmaf(-a1[i], a1[i], 1.f) * gb;
+        ze1[i] = (-2.f * a1[i]) * g1[i] * gb;          // phi'' u1 gbar1
+        v[i] = ub1[i];
+      }
+    }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(0))
+    EPDE_P2_WAIT()
+    // ---- S7: ubar2 -> gbar3 = W3 ubar2;  round 1 is staged while that MMA runs ---------------------------
+    tm_ld20(tl + dcol, z);
+    float ub2[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      ub2[i] = fmaf(-a2[i], a2[i], 1.f) * z[i];
+      ze2[i] = (-2.f * a2[i]) * g2[i] * z[i];
+      v[i] = ub2[i];
+    }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(1))
+    {
+      const uint32_t T = acquire();
+      flush1();
+#pragma unroll
+      for (int i = 0; i < H; i++) {
+        stage_val(sM, i, g2[i]);
+        stage_val(sM, 20 + i, fmaf(-a3[i], a3[i], 1.f) * sw[L.w4() + i]);
+        stage_val(sM, 40 + i, ebar * g1[i]);
+        stage_val(sN, i, ub1[i]);
+        stage_val(sN, 20 + i, ub2[i]);
+        stage_val(sN, 40 + i, g1[i]);
+      }
+      EPDE_P2_ROUND_ISSUE(T, issue_round<64>(tm + D1, sgb))
+    }
+    EPDE_P2_WAIT()
+    // ---- S8: zbar3, s4 -> W3^T zbar3 -------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+    float zb3[H], s4[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const float t3 = fmaf(-a3[i], a3[i], 1.f);
+      s4[i] = fmaf(ybar, a3[i], t3 * z[i]);                              // ubar3 + ybar a3  (d / d w4)
+      zb3[i] = (t3 * sw[L.w4() + i]) * fmaf(-2.f * a3[i], z[i], ybar);   // g3 (-2 a3 gbar3 + ybar)
+      v[i] = zb3[i];
+    }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(3))
+    EPDE_P2_WAIT()
+    // ---- S9: zbar2 -> W2^T zbar2;  round 2 is staged while that MMA runs ----------------------------------
+    tm_ld20(tl + dcol, z);
+    float zb2[H];
+#pragma unroll
+    for (int i = 0; i < H; i++) { zb2[i] = fmaf(fmaf(-a2[i], a2[i], 1.f), z[i], ze2[i]); v[i] = zb2[i]; }
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_ISSUE(EPDE_P2_MV(2))
+    {
+      const uint32_t T = acquire();
+      flush2();
+#pragma unroll
+      for (int i = 0; i < H; i++) {
+        stage_val(sM, i, zb2[i]);
+        stage_val(sM, 20 + i, zb3[i]);
+        stage_val(sM, 40 + i, s4[i]);
+        stage_val(sN, i, a1[i]);
+        stage_val(sN, 21 + i, a2[i]);
+      }
+      stage_val(sM, 60, ybar);                          // rows 61..63 / columns 42..47 hold stale finite values: ignored
+      stage_val(sN, 20, 1.f); stage_val(sN, 41, 1.f);
+      EPDE_P2_ROUND_ISSUE(T, issue_round<48>(tm + D2, sgb))
+    }
+    EPDE_P2_WAIT()
+    // ---- S10: zbar1;  round 3 ----------------------------------------------------------------------------
+    tm_ld20(tl + dcol, z);
+    {
+      float xv[64];
+#pragma unroll
+      for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
+      const uint32_t T = acquire();
+      flush3();
+#pragma unroll
+      for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
+#pragma unroll
+      for (int j = 0; j < 64; j++) if (j < K1) stage_val(sN, j, xv[j]);
+      EPDE_P2_ROUND_ISSUE(T, issue_round_rt(ks1, tm + D3, sgb))
+    }
+  }
+#undef EPDE_P2_ROUND_ISSUE
+#undef EPDE_P2_ISSUE
+#undef EPDE_P2_WAIT
+#undef EPDE_P2_MV
+  // ---- all rounds done: last flush, per-CTA gradient image -> global ----------------------------------------
+  fence_before();
+  __syncthreads();
+  fence_after();
+  {
+    const uint32_t total = slot[1];
+    if (g == 0) {
+      if (total > 0) mbar_wait(ring + ((total - 1) & 3), ((total - 1) >> 2) & 1);
+      fence_after();
+      flush1(); flush2(); flush3();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;
+  for (int i = tid; i < gn; i += P2THREADS) dst[i] = acc[i];
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tm));
+}
+
+}  // namespace tc
+}  // namespace epde

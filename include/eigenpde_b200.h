@@ -173,6 +173,14 @@ int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d
                             const double* d_out_scalars, void* stream);
 int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
 
+/*
+ * Kernel family of the fused path (reference architecture d -> 20 -> 20 -> 20 -> 1, Tanh):
+ *   0  FP32 FFMA2 kernels, sample-pair threads, weights broadcast from shared memory
+ *   1  tcgen05 (kind::tf32, 3xTF32 split) kernels, thread = TMEM lane = sample
+ * Both compute the same quantities to the same tolerance; the switch is process-wide.
+ */
+int epde_set_fused_impl(int impl);
+
 #ifdef __cplusplus
 }
 #endif
