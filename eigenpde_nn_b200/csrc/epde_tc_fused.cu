@@ -48,7 +48,7 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * P2G > nt128) gx = (int)((nt128 + P2G - 1) / P2G);
   const int gn = GradLayout<TH>(d_pad).total();
-  const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)((gn + 7) & ~7) * 4 + 128;
+  const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2_ACC2 * 4 + 128;
   cudaError_t e = cudaFuncSetAttribute(k_pass2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   k_pass2_tc<<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg);

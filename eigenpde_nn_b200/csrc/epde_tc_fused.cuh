@@ -22,9 +22,11 @@ namespace tc {
 
 #ifdef EPDE_PHASE_TIMING
 __device__ unsigned long long g_tc_cycles[16];
-#define TC_T0() long long tt_ = clock64()
+#define TC_DECL() long long tt_ = 0
+#define TC_T0() tt_ = clock64()
 #define TC_ADD(slot) do { long long n_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_tc_cycles[slot], (unsigned long long)(n_ - tt_)); tt_ = n_; } while (0)
 #else
+#define TC_DECL() do {} while (0)
 #define TC_T0() do {} while (0)
 #define TC_ADD(slot) do {} while (0)
 #endif
@@ -289,6 +291,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   uint64_t* bar = bars + g;
   uint32_t ph = 0;
   double accS = 0.0, accE = 0.0;
+  TC_DECL();
 
   const int64_t nt128 = (B + 127) / 128;
   // the x block of a tile ([j][128], contiguous in the 128-tile-major gather copy) travels global -> shared as ONE

@@ -28,6 +28,8 @@ constexpr int SG_ROWS = 64;                     // rows per image
 constexpr uint32_t SG_IMG = (SG_ROWS / 8) * SG_SBO;   // one image (hi or lo) = 36864 B
 // staging buffer: [M hi][M lo][N hi][N lo]
 constexpr uint32_t SG_BYTES = 4 * SG_IMG;
+constexpr int P2_S1 = 65, P2_S2 = 49, P2_S3 = 65;   // row strides of the raw accumulator images (odd: conflict-free)
+constexpr int P2_ACC2 = 64 * P2_S1 + 64 * P2_S2 + 20 * P2_S3;   // raw per-CTA accumulator images of the three round types
 
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
@@ -38,6 +40,8 @@ __device__ __forceinline__ void stage_val(uint32_t img_hi, int r, float v) {
   const uint32_t o = (uint32_t)(r >> 3) * SG_SBO + (uint32_t)(r & 7) * 16u;
   sts32(img_hi + o, hi); sts32(img_hi + SG_IMG + o, lo);
 }
+
+__device__ __forceinline__ void accadd(float* p, float v) { *p += v; }
 
 // one gradient round: D[64 x N] = sum over 128 samples, 3xTF32, small terms first; fresh accumulator
 template <int N>
@@ -77,15 +81,16 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   const int gn = G.total();
   unsigned char* sg = tsm;                                          // staging buffer (SG_BYTES)
   float* sw = reinterpret_cast<float*>(tsm + SG_BYTES);             // packed weights
-  float* acc = sw + L.total();                                      // per-CTA gradient image (GradLayout)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(acc + ((gn + 7) & ~7));   // [P2G] mat-vec, [4] round ring
+  float* acc = reinterpret_cast<float*>(sg);                        // per-CTA gradient image (GradLayout): built at the END in the (then idle) staging buffer
+  float* acc2 = sw + L.total();                                     // raw accumulator images (see flush*)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(acc2 + P2_ACC2);     // [P2G] mat-vec, [4] round ring
   uint32_t* slot = reinterpret_cast<uint32_t*>(bars + P2G + 4);     // [0] tmem base, [1] ticket, [2..] ticket of group
   const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, wq = warp & 3, lane = tid & 31, net = blockIdx.y;
   const int sn = tid & 127;                                         // sample within the tile = TMEM lane
   {
     const float* src = pwt + (size_t)net * L.total();
     for (int i = tid; i < L.total(); i += P2THREADS) sw[i] = src[i];
-    for (int i = tid; i < gn; i += P2THREADS) acc[i] = 0.f;
+    for (int i = tid; i < P2_ACC2; i += P2THREADS) acc2[i] = 0.f;
     for (uint32_t i = tid; i < SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
   }
   if (tid == 0) { for (int i = 0; i < P2G + 4; i++) mbar_init(bars + i, 1); slot[1] = 0; }
@@ -98,10 +103,11 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   fence_before(); __syncthreads(); fence_after();
   const uint32_t tm = slot[0];
   const int K1 = L.K1(), ks1 = L.ks1;
-  const int KA = K1 > TKH ? K1 : TKH;
-  const uint32_t gc = (uint32_t)g * (2 * KA + TN);
+  const int KA = K1 > 56 ? K1 : 56;                                  // A region: x (K1 columns); hidden vectors use 24 of them,
+  const uint32_t gc = (uint32_t)g * (2 * KA + TN);                   // columns 24..43 of the hi and lo halves park long-lived vectors
   const uint32_t tl = tm + ((uint32_t)(wq * 32) << 16);
   const uint32_t ahi = gc, alo = gc + KA, dcol = gc + 2 * KA;
+  const uint32_t pkA = tl + ahi + 24, pkB = tl + alo + 24;           // parking slots (20 columns each)
   const uint32_t gbase = (uint32_t)P2G * (2 * KA + TN);             // gradient accumulators: D1 (64), D2 (48), D3 (K1)
   const uint32_t D1 = gbase, D2 = gbase + 64, D3 = gbase + 112;
   {  // zero the accumulators once (the first flush of every round type adds them)
@@ -112,41 +118,38 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   }
   const uint32_t idesc = idesc_tf32(128, TN);
   const uint32_t sbase = smem_u32(sw), sgb = smem_u32(sg);
-  const uint64_t dW1h = kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32), dW1l = kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32);
-  uint64_t dMh[5], dMl[5];
-#pragma unroll
-  for (int m = 0; m < 5; m++) {
-    dMh[m] = kdesc(sbase + L.mat(m, 0) * 4, 128, TKH * 32); dMl[m] = kdesc(sbase + L.mat(m, 1) * 4, 128, TKH * 32);
-  }
   const float b4r = sw[L.b4()];
   const float ecoef = coef->ecoef[net], cm = coef->cm[net];
-  float cw[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) cw[j] = (j < K) ? coef->Cw[net][j] : 0.f;
   uint64_t* bar = bars + g;
   uint64_t* ring = bars + P2G;
   uint32_t ph = 0;
+  TC_DECL();
   // this thread's column inside a staging image
   const uint32_t tcol = (uint32_t)(sn >> 2) * SG_LBO + (uint32_t)(sn & 3) * 4u;
   const uint32_t sM = sgb + tcol, sN = sgb + 2 * SG_IMG + tcol;
   fence_before(); __syncthreads(); fence_after();
 
   // ---- flush of a round's accumulator (M = 64 layout: row r in lane (r / 16) * 32 + r % 16) into acc ----------
+  // Only the holder of the staging buffer runs this, so plain read-modify-write is safe; every chunk is
+  // load-all / add-all / store-all (a chain of dependent shared-memory RMWs costs ~60 cycles per element).
+  auto rmw16 = [&](float* p, const float* v, bool on) {      // p[0..15] += v[0..15]
+    if (on) {
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) o[i] = p[i];
+#pragma unroll
+      for (int i = 0; i < 16; i++) p[i] = o[i] + v[i];
+    }
+  };
+  // acc image used while the kernel runs: the three accumulators verbatim, [row][col] with 64 / 48 / 64 columns
+  //   A1 = acc2 + 0, A2 = acc2 + 64 * 64, A3 = acc2 + 64 * 64 + 64 * 48
   auto flush1 = [&]() {       // D1: rows g2 | g3 | ebar g1, cols ubar1 | ubar2 | g1
     const int r = 16 * wq + lane;
     float v[16];
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 16) {
       tm_ld16(tl + D1 + c0, v); wait_ld();
-      if (lane < 16) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const int c = c0 + i;
-          if (c < 20) { if (r < 20) atomicAdd(acc + G.gW2() + r * H + c, v[i]); }
-          else if (c < 40) { if (r >= 20 && r < 40) atomicAdd(acc + G.gW3() + (r - 20) * H + (c - 20), v[i]); }
-          else if (c < 60) { if (r >= 40 && r < 60) atomicAdd(acc + G.Gam() + (r - 40) * H + (c - 40), v[i]); }
-        }
-      }
+      rmw16(acc2 + r * P2_S1 + c0, v, lane < 16);
     }
   };
   auto flush2 = [&]() {       // D2: rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
@@ -155,20 +158,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
     for (int c0 = 0; c0 < 48; c0 += 16) {
       tm_ld16(tl + D2 + c0, v); wait_ld();
-      if (lane < 16) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const int c = c0 + i;
-          if (c < 20) { if (r < 20) atomicAdd(acc + G.gW2() + r * H + c, v[i]); }
-          else if (c == 20) {
-            if (r < 20) atomicAdd(acc + G.gb2() + r, v[i]);
-            else if (r >= 40 && r < 60) atomicAdd(acc + G.gw4() + (r - 40), v[i]);
-            else if (r == 60) atomicAdd(acc + G.gb4(), v[i]);
-          }
-          else if (c < 41) { if (r >= 20 && r < 40) atomicAdd(acc + G.gW3() + (r - 20) * H + (c - 21), v[i]); }
-          else if (c == 41) { if (r >= 20 && r < 40) atomicAdd(acc + G.gb3() + (r - 20), v[i]); }
-        }
-      }
+      rmw16(acc2 + 64 * P2_S1 + r * P2_S2 + c0, v, lane < 16);
     }
   };
   auto flush3 = [&]() {       // D3: rows zbar1, cols x | 1
@@ -177,14 +167,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll 1
     for (int c0 = 0; c0 < K1; c0 += 16) {
       tm_ld16(tl + D3 + c0, v); wait_ld();
-      if (lane < 16 && r < 20) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const int c = c0 + i;
-          if (c < d) atomicAdd(acc + G.gW1() + r * d_pad + c, v[i]);
-          else if (c == d) atomicAdd(acc + G.gb1() + r, v[i]);
-        }
-      }
+      rmw16(acc2 + 64 * P2_S1 + 64 * P2_S2 + r * P2_S3 + c0, v, lane < 16 && r < 20);
     }
   };
   // take the staging buffer: ticket T, wait for round T-1 (its MMAs have read the buffer and written their D)
@@ -192,20 +175,23 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     if (sn == 0) slot[2 + g] = atomicAdd(slot + 1, 1u);
     group_bar(g);
     const uint32_t T = slot[2 + g];
+    TC_ADD(0);
     if (T > 0) mbar_wait(ring + ((T - 1) & 3), ((T - 1) >> 2) & 1);
     fence_after();
+    TC_ADD(5);
     return T;
   };
 #define EPDE_P2_ROUND_ISSUE(T, ISSUE)                                                                  \
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                     \
-    fence_before(); group_bar(g);                                                                    \
-    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); }
+    TC_ADD(7); asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
+    fence_before(); group_bar(g); TC_ADD(1);                                                         \
+    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); } TC_ADD(8);
 
 #define EPDE_P2_ISSUE(ISSUE)                                                                         \
-    fence_before(); group_bar(g);                                                                    \
-    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(bar); } __syncwarp(); }
-#define EPDE_P2_WAIT() mbar_wait(bar, ph); ph ^= 1; fence_after();
-#define EPDE_P2_MV(m) issue_matvec<3>(tm + dcol, tm + ahi, tm + alo, dMh[m], dMl[m], idesc)
+    TC_ADD(0); fence_before(); group_bar(g); TC_ADD(1);                                              \
+    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(bar); } __syncwarp(); } TC_ADD(2);
+#define EPDE_P2_WAIT() mbar_wait(bar, ph); ph ^= 1; fence_after(); TC_ADD(3);
+#define EPDE_P2_MV(m) issue_matvec<3>(tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.mat(m, 0) * 4, 128, TKH * 32), \
+                                      kdesc(sbase + L.mat(m, 1) * 4, 128, TKH * 32), idesc)
 
   const int64_t nt128 = (B + 127) / 128;
   const int64_t tstep = (int64_t)gridDim.x * P2G;
@@ -217,10 +203,11 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     float ybar = -cm;
     if (n < B) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) if (j < K) ybar = fmaf(cw[j], __ldg(ybuf + n * K + j), ybar);
+      for (int j = 0; j < 8; j++) if (j < K) ybar = fmaf(coef->Cw[net][j], __ldg(ybuf + n * K + j), ybar);
     }
     ybar *= wn;                                     // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
     const float ebar = wn * ecoef;
+    TC_T0();
     // ---- S0: x -> A -------------------------------------------------------------------------------
     {
       float xv[64];
@@ -237,7 +224,9 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       }
       wait_st();
     }
-    EPDE_P2_ISSUE(issue_matvec_rt(ks1, tm + dcol, tm + ahi, tm + alo, dW1h, dW1l, idesc))
+    TC_ADD(4);
+    EPDE_P2_ISSUE(issue_matvec_rt(ks1, tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32),
+                                  kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32), idesc))
     EPDE_P2_WAIT()
     float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
     v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
@@ -245,6 +234,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     tm_ld20(tl + dcol, z);
 #pragma unroll
     for (int i = 0; i < H; i++) { a1[i] = tanh1(z[i]); v[i] = a1[i]; }
+    tm_st16(pkA, a1); tm_st4(pkA + 16, a1 + 16);        // a1 is parked in TMEM until S5
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(0))
     EPDE_P2_WAIT()
@@ -270,6 +260,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(2))
     EPDE_P2_WAIT()
     // ---- S5: g1 -> K g1 -----------------------------------------------------------------------------
+    tm_ld16(pkA, a1); tm_ld4(pkA + 16, a1 + 16);
     tm_ld20(tl + dcol, z);
 #pragma unroll
     for (int i = 0; i < H; i++) { g1[i] = fmaf(-a1[i], a1[i], 1.f) * z[i]; v[i] = g1[i]; }
@@ -289,6 +280,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
         v[i] = ub1[i];
       }
     }
+    tm_st16(pkB, ze1); tm_st4(pkB + 16, ze1 + 16);      // phi'' term of zbar1: parked until S10 (a1 stays parked in pkA)
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(0))
     EPDE_P2_WAIT()
@@ -305,7 +297,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(1))
     {
       const uint32_t T = acquire();
-      flush1();
+      flush1(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, g2[i]);
@@ -332,6 +324,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(3))
     EPDE_P2_WAIT()
     // ---- S9: zbar2 -> W2^T zbar2;  round 2 is staged while that MMA runs ----------------------------------
+    tm_ld16(pkA, a1); tm_ld4(pkA + 16, a1 + 16);
     tm_ld20(tl + dcol, z);
     float zb2[H];
 #pragma unroll
@@ -340,7 +333,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(2))
     {
       const uint32_t T = acquire();
-      flush2();
+      flush2(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, zb2[i]);
@@ -355,13 +348,15 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     }
     EPDE_P2_WAIT()
     // ---- S10: zbar1;  round 3 ----------------------------------------------------------------------------
+    tm_ld16(pkB, ze1); tm_ld4(pkB + 16, ze1 + 16);
     tm_ld20(tl + dcol, z);
     {
       float xv[64];
 #pragma unroll
       for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
+      TC_ADD(9);
       const uint32_t T = acquire();
-      flush3();
+      flush3(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
 #pragma unroll
@@ -386,6 +381,27 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     }
   }
   fence_before();
+  __syncthreads();
+  {  // raw accumulator images -> GradLayout image of this CTA
+    const float* A1 = acc2; const float* A2 = acc2 + 64 * P2_S1; const float* A3 = A2 + 64 * P2_S2;
+    for (int e = tid; e < H * H; e += P2THREADS) {
+      const int r = e / H, c = e % H;
+      acc[G.gW2() + e] = A1[r * P2_S1 + c] + A2[r * P2_S2 + c];
+      acc[G.gW3() + e] = A1[(20 + r) * P2_S1 + 20 + c] + A2[(20 + r) * P2_S2 + 21 + c];
+      acc[G.Gam() + e] = A1[(40 + r) * P2_S1 + 40 + c];
+    }
+    for (int e = tid; e < H * d_pad; e += P2THREADS) {
+      const int r = e / d_pad, c = e % d_pad;
+      acc[G.gW1() + e] = (c < d) ? A3[r * P2_S3 + c] : 0.f;
+    }
+    for (int r = tid; r < H; r += P2THREADS) {
+      acc[G.gb1() + r] = A3[r * P2_S3 + d];
+      acc[G.gb2() + r] = A2[r * P2_S2 + 20];
+      acc[G.gb3() + r] = A2[(20 + r) * P2_S2 + 41];
+      acc[G.gw4() + r] = A2[(40 + r) * P2_S2 + 20];
+    }
+    if (tid == 0) acc[G.gb4()] = A2[60 * P2_S2 + 20];
+  }
   __syncthreads();
   float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;
   for (int i = tid; i < gn; i += P2THREADS) dst[i] = acc[i];
