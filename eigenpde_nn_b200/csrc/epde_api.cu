@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
 constexpr int kFusedH = 20;
-int g_fused_impl = 0;                  // 0: FFMA2 kernels (epde_fused.cuh)   1: tcgen05 kernels (epde_tc_fused.cuh)
+int g_fused_impl = 1;                  // 1: tcgen05 kernels (epde_tc_fused.cuh, default)   0: FFMA2 kernels (epde_fused.cuh)
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
@@ -115,7 +115,7 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
                   const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
-  k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
+  if (g_fused_impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
   cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, g_fused_impl == 1);
   if (e != cudaSuccess) return (int)e;
   if (g_fused_impl == 1)

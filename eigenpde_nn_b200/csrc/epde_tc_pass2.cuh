@@ -143,33 +143,24 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   };
   // acc image used while the kernel runs: the three accumulators verbatim, [row][col] with 64 / 48 / 64 columns
   //   A1 = acc2 + 0, A2 = acc2 + 64 * 64, A3 = acc2 + 64 * 64 + 64 * 48
-  auto flush1 = [&]() {       // D1: rows g2 | g3 | ebar g1, cols ubar1 | ubar2 | g1
+  // two 16-column chunks per tcgen05.wait::ld
+  auto flush_rows = [&](uint32_t dcol0, float* base, int stride, int ncol, bool on) {
     const int r = 16 * wq + lane;
-    float v[16];
+    float v[32];
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      tm_ld16(tl + D1 + c0, v); wait_ld();
-      rmw16(acc2 + r * P2_S1 + c0, v, lane < 16);
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      if (c0 < ncol) {
+        tm_ld16(tl + dcol0 + c0, v);
+        if (c0 + 16 < ncol) tm_ld16(tl + dcol0 + c0 + 16, v + 16);
+        wait_ld();
+        rmw16(base + r * stride + c0, v, on);
+        if (c0 + 16 < ncol) rmw16(base + r * stride + c0 + 16, v + 16, on);
+      }
     }
   };
-  auto flush2 = [&]() {       // D2: rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
-    const int r = 16 * wq + lane;
-    float v[16];
-#pragma unroll
-    for (int c0 = 0; c0 < 48; c0 += 16) {
-      tm_ld16(tl + D2 + c0, v); wait_ld();
-      rmw16(acc2 + 64 * P2_S1 + r * P2_S2 + c0, v, lane < 16);
-    }
-  };
-  auto flush3 = [&]() {       // D3: rows zbar1, cols x | 1
-    const int r = 16 * wq + lane;
-    float v[16];
-#pragma unroll 1
-    for (int c0 = 0; c0 < K1; c0 += 16) {
-      tm_ld16(tl + D3 + c0, v); wait_ld();
-      rmw16(acc2 + 64 * P2_S1 + 64 * P2_S2 + r * P2_S3 + c0, v, lane < 16 && r < 20);
-    }
-  };
+  auto flush1 = [&]() { flush_rows(D1, acc2, P2_S1, 64, lane < 16); };                       // rows g2 | g3 | ebar g1, cols ubar1 | ubar2 | g1
+  auto flush2 = [&]() { flush_rows(D2, acc2 + 64 * P2_S1, P2_S2, 48, lane < 16); };          // rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
+  auto flush3 = [&]() { flush_rows(D3, acc2 + 64 * P2_S1 + 64 * P2_S2, P2_S3, K1, lane < 16 && 16 * wq + lane < 20); };   // rows zbar1, cols x | 1
   // take the staging buffer: ticket T, wait for round T-1 (its MMAs have read the buffer and written their D)
   auto acquire = [&]() -> uint32_t {
     if (sn == 0) slot[2 + g] = atomicAdd(slot + 1, 1u);
@@ -182,7 +173,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     return T;
   };
 #define EPDE_P2_ROUND_ISSUE(T, ISSUE)                                                                  \
-    TC_ADD(7); asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
     fence_before(); group_bar(g); TC_ADD(1);                                                         \
     if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); } TC_ADD(8);
 
@@ -297,7 +288,6 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(1))
     {
       const uint32_t T = acquire();
-      flush1(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, g2[i]);
@@ -307,6 +297,8 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
         stage_val(sN, 20 + i, ub2[i]);
         stage_val(sN, 40 + i, g1[i]);
       }
+      TC_ADD(7);
+      flush1(); TC_ADD(6);
       EPDE_P2_ROUND_ISSUE(T, issue_round<64>(tm + D1, sgb))
     }
     EPDE_P2_WAIT()
@@ -333,7 +325,6 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     EPDE_P2_ISSUE(EPDE_P2_MV(2))
     {
       const uint32_t T = acquire();
-      flush2(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, zb2[i]);
@@ -344,6 +335,8 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       }
       stage_val(sM, 60, ybar);                          // rows 61..63 / columns 42..47 hold stale finite values: ignored
       stage_val(sN, 20, 1.f); stage_val(sN, 41, 1.f);
+      TC_ADD(7);
+      flush2(); TC_ADD(6);
       EPDE_P2_ROUND_ISSUE(T, issue_round<48>(tm + D2, sgb))
     }
     EPDE_P2_WAIT()
@@ -356,11 +349,12 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
       TC_ADD(9);
       const uint32_t T = acquire();
-      flush3(); TC_ADD(6);
 #pragma unroll
       for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
 #pragma unroll
       for (int j = 0; j < 64; j++) if (j < K1) stage_val(sN, j, xv[j]);
+      TC_ADD(7);
+      flush3(); TC_ADD(6);
       EPDE_P2_ROUND_ISSUE(T, issue_round_rt(ks1, tm + D3, sgb))
     }
   }
