@@ -65,10 +65,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
 #pragma unroll 1
-  for (int it = 0; it < (1 << 24); it++) {
+  for (int it = 0; it < (1 << 19); it++) {          // x 2 us suspend hint = ~1 s
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+                 "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(ok) : "r"(a), "r"(parity), "r"(2000u) : "memory");    // suspend-time hint (ns)
     if (ok) return;
   }
   __trap();

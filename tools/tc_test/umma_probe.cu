@@ -268,6 +268,30 @@ k_probe(const float* __restrict__ A, const float* __restrict__ W, const float* _
     if (t0) out->cyc[t] = clock64() - t0;
   }
 
+  // ---------------- test G: issue-side blocking: cycles the issuing thread needs to ISSUE n SS-MMAs (M64 N64) -----
+  for (int t = 0; t < 6; t++) {
+    fence_before(); __syncthreads();
+    long long t0 = 0, t1 = 0;
+    if (warp == 0 && elect_one()) {
+      fence_after();
+      const uint32_t KG = 128 / 4 * 128, FG = 128;
+      const uint64_t da = make_desc(smem_u32(Phi), KG, FG), db = make_desc(smem_u32(Plo), KG, FG);
+      const uint32_t id = make_idesc(64, 64, 0, 0);
+      const int n = 4 << t;                                  // 4, 8, 16, 32, 64, 128
+      t0 = clock64();
+#pragma unroll 1
+      for (int r = 0; r < n; r += 4) {
+        mma_ss(tm + 256, da, db, id, 1u); mma_ss(tm + 256, da, db, id, 1u);
+        mma_ss(tm + 256, da, db, id, 1u); mma_ss(tm + 256, da, db, id, 1u);
+      }
+      t1 = clock64();
+      commit(bar);
+    }
+    if (!mbar_wait(bar, phase)) { out->fail = 40 + t; return; }
+    phase ^= 1; fence_after();
+    if (t0) { out->cyc[10 + t] = ((t1 - t0) << 24) | (clock64() - t0); }
+  }
+
   // ---------------- test D: accumulator rounding ------------------------------------------------
   // D = 1.0, then 64 x (+ 1.5 * 2^-24): round-to-nearest gives 1 + 64 * 2^-23, truncation leaves 1.0
   {
@@ -370,6 +394,7 @@ int main() {
     printf("\n");
     const char* names[7] = {"TS M128 N32", "SS M128 N32", "SS M128 N64", "SS M128 N128", "SS M64 N32", "TS N32 + SS N64 alternating", "SS M128 N96"};
     for (int t = 0; t < 7; t++) printf("  C %-28s %.1f cycles/MMA\n", names[t], o.cyc[t] / 512.0);
+    for (int t = 0; t < 6; t++) printf("  G issue %3d MMAs (M64 N64 SS): issue done after %lld cycles, all complete after %lld\n", 4 << t, o.cyc[10 + t] >> 24, o.cyc[10 + t] & 0xFFFFFF);
     printf("  D accumulator: D-1 = %.3e (RN expects %.3e, RZ expects 0); exact col = %.3e\n", o.acc[0], 64 * ldexp(1.0, -23), o.acc[1]);
     printf("  E tcgen05.ld x32: %.1f cycles per instr/warp (4 warps)   tcgen05.st 4x x8: %.1f cycles\n", o.cyc[8] / 256.0, o.cyc[9] / 256.0);
   }
