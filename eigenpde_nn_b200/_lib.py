@@ -16,6 +16,7 @@ EPDE_MAX_K = 8
 ACT_IDS = {"Tanh": 0, "Sigmoid": 1, "Softplus": 2, "LogSigmoid": 3, "ELU": 4, "CELU": 4, "ReLU": 5,
            "Tanhshrink": 6}
 FLAG_SORT = 1
+FLAG_DETERMINISTIC = 2
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
@@ -73,7 +74,7 @@ def check(rc: int, what: str):
         raise EpdeError("%s failed: %d (%s)" % (what, rc, lib().epde_error_string(rc).decode()))
 
 
-def make_desc(arch, k, activation_name, d_pad, sort=True) -> EpdeDesc:
+def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False) -> EpdeDesc:
     """arch = [d, n_1, ..., n_{L-1}, 1] (src/pytorch_eigen_solver.py:352)."""
     if len(arch) - 1 > EPDE_MAX_LAYERS:
         raise EpdeError("too many layers")
@@ -83,5 +84,5 @@ def make_desc(arch, k, activation_name, d_pad, sort=True) -> EpdeDesc:
         D.widths[i] = int(n)
     # unknown activation names fall back to CELU in the reference (src/network_arch.py:27-32)
     D.act_id = ACT_IDS.get(activation_name, ACT_IDS["CELU"])
-    D.flags = FLAG_SORT if sort else 0
+    D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0)
     return D

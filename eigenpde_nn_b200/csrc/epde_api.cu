@@ -149,7 +149,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
   if (g_fused_impl == 1) {
     int gx = 0;
-    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx, st);
+    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx,
+                    (D->flags & EPDE_FLAG_DETERMINISTIC) ? 1 : 0, st);
     if (rc) return rc;
     const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
     k_fin2<kFusedH><<<D->k, 512, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);

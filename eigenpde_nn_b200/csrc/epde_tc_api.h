@@ -17,7 +17,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 
 // phase 2: k_pass2_tc -> per-CTA gradient images pg[(cta * k + net) * GradLayout.total()], *gx_out = CTAs per net
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
-           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st);
+           const float* ybuf, const Coef* coef, float* pg, int* gx_out, int fixed_order, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace epde

@@ -42,7 +42,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 }
 
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
-           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st) {
+           const float* ybuf, const Coef* coef, float* pg, int* gx_out, int fixed_order, cudaStream_t st) {
   const TcPack TL(d);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
@@ -51,7 +51,7 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2_ACC2 * 4 + 128;
   cudaError_t e = cudaFuncSetAttribute(k_pass2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k_pass2_tc<<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg);
+  k_pass2_tc<<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order);
   *gx_out = gx;
   return (int)cudaGetLastError();
 }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void issue_round_rt(int n8, uint32_t d_t, uint32_t sg
 __global__ void __launch_bounds__(P2THREADS, 1)
 k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad, int K,
            const float* __restrict__ pwt, const float* __restrict__ ybuf, const Coef* __restrict__ coef,
-           float* __restrict__ pg) {
+           float* __restrict__ pg, int fixed_order) {
   constexpr int H = TH;
   extern __shared__ __align__(1024) unsigned char tsm[];
   const TcPack L(d);
@@ -86,7 +86,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   float* acc = reinterpret_cast<float*>(sg);                        // per-CTA gradient image (GradLayout): built at the END in the (then idle) staging buffer
   float* acc2 = sw + L.total();                                     // raw accumulator images (see flush*)
   uint64_t* bars = reinterpret_cast<uint64_t*>(acc2 + P2_ACC2);     // [P2G] mat-vec, [4] round ring
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + P2G + 4);     // [0] tmem base, [1] ticket, [2..] ticket of group
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + P2G + 4);     // [0] tmem base, [1] ticket, [2..3] ticket of group, [4..6] turn of round type
   const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, wq = warp & 3, lane = tid & 31, net = blockIdx.y;
   const int sn = tid & 127;                                         // sample within the tile = TMEM lane
   {
@@ -95,7 +95,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     for (int i = tid; i < P2_ACC2; i += P2THREADS) acc2[i] = 0.f;
     for (uint32_t i = tid; i < SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
   }
-  if (tid == 0) { for (int i = 0; i < P2G + 4; i++) mbar_init(bars + i, 1); slot[1] = 0; }
+  if (tid == 0) { for (int i = 0; i < P2G + 4; i++) mbar_init(bars + i, 1); slot[1] = 0; slot[4] = 0; slot[5] = 0; slot[6] = 0; }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -164,8 +164,18 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   auto flush2 = [&]() { flush_rows(D2, acc2 + 64 * P2_S1, P2_S2, 48, lane < 16); };          // rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
   auto flush3 = [&]() { flush_rows(D3, acc2 + 64 * P2_S1 + 64 * P2_S2, P2_S3, K1, lane < 16 && 16 * wq + lane < 20); };   // rows zbar1, cols x | 1
   // take the staging buffer: ticket T, wait for round T-1 (its MMAs have read the buffer and written their D)
-  auto acquire = [&]() -> uint32_t {
-    if (sn == 0) slot[2 + g] = atomicAdd(slot + 1, 1u);
+  // With fixed_order (EPDE_FLAG_DETERMINISTIC) rounds of one type are taken in a FIXED order (group 0 tile i, group 1 tile i, group 0 tile i+1, ...), so the
+  // order in which tile contributions are added to the accumulator images - and with it every bit of the
+  // gradient - does not depend on how the two groups happen to interleave.
+  auto acquire = [&](int r, uint32_t want) -> uint32_t {
+    if (sn == 0) {
+      uint32_t cur = want; int spin = 0;
+      if (fixed_order) do {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(cur) : "r"(smem_u32(slot + 4 + r)) : "memory");
+        if (cur != want) { __nanosleep(32); if (++spin > (1 << 24)) __trap(); }
+      } while (cur != want);
+      slot[2 + g] = atomicAdd(slot + 1, 1u);
+    }
     group_bar(g);
     const uint32_t T = slot[2 + g];
     TC_ADD(0);
@@ -174,10 +184,12 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     TC_ADD(5);
     return T;
   };
-#define EPDE_P2_ROUND_ISSUE(T, ISSUE)                                                                  \
+#define EPDE_P2_ROUND_ISSUE(T, RT, ISSUE)                                                                  \
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
     fence_before(); group_bar(g); TC_ADD(1);                                                         \
-    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); } TC_ADD(8);
+    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); }          \
+    if (fixed_order && sn == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(smem_u32(slot + 4 + RT)), "r"(turn_next) : "memory"); \
+    TC_ADD(8);
 
 #define EPDE_P2_ISSUE(ISSUE)                                                                         \
     TC_ADD(0); fence_before(); group_bar(g); TC_ADD(1);                                              \
@@ -192,6 +204,10 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   for (int64_t t = (int64_t)blockIdx.x * P2G + g; t < nt128; t += tstep) {
     const int64_t n = t * 128 + sn;
     const float* xcol = xt + (size_t)t * d_pad * 128 + sn;
+    // turn numbers of this tile's rounds: 2 * (local tile index) + group; group 0 skips the other group's turn when
+    // that group has no tile of the same index (only possible for the last one)
+    const uint32_t turn_want = 2u * (uint32_t)((t - ((int64_t)blockIdx.x * P2G + g)) / tstep) + (uint32_t)g;
+    const uint32_t turn_next = turn_want + ((g == 0 && t + 1 >= nt128) ? 2u : 1u);
     const float wn = __ldg(wt + n);
     float ybar = -cm;
     if (n < B) {
@@ -289,7 +305,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(1))
     {
-      const uint32_t T = acquire();
+      const uint32_t T = acquire(0, turn_want);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, g2[i]);
@@ -301,7 +317,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       }
       TC_ADD(7);
       flush1(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, issue_round<64>(tm + D1, sgb))
+      EPDE_P2_ROUND_ISSUE(T, 0, issue_round<64>(tm + D1, sgb))
     }
     EPDE_P2_WAIT()
     // ---- S8: zbar3, s4 -> W3^T zbar3 -------------------------------------------------------------------
@@ -326,7 +342,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(2))
     {
-      const uint32_t T = acquire();
+      const uint32_t T = acquire(1, turn_want);
 #pragma unroll
       for (int i = 0; i < H; i++) {
         stage_val(sM, i, zb2[i]);
@@ -339,7 +355,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       stage_val(sN, 20, 1.f); stage_val(sN, 41, 1.f);
       TC_ADD(7);
       flush2(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, issue_round<48>(tm + D2, sgb))
+      EPDE_P2_ROUND_ISSUE(T, 1, issue_round<48>(tm + D2, sgb))
     }
     EPDE_P2_WAIT()
     // ---- S10: zbar1;  round 3 ----------------------------------------------------------------------------
@@ -350,14 +366,14 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
       for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
       TC_ADD(9);
-      const uint32_t T = acquire();
+      const uint32_t T = acquire(2, turn_want);
 #pragma unroll
       for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
 #pragma unroll
       for (int j = 0; j < 64; j++) if (j < K1) stage_val(sN, j, xv[j]);
       TC_ADD(7);
       flush3(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, issue_round_rt(ks1, tm + D3, sgb))
+      EPDE_P2_ROUND_ISSUE(T, 2, issue_round_rt(ks1, tm + D3, sgb))
     }
   }
 #undef EPDE_P2_ROUND_ISSUE

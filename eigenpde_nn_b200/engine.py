@@ -33,7 +33,7 @@ class StepEngine:
     """
 
     def __init__(self, X, weights, arch, k, activation_name, diag_coeff, beta, eig_w, sort=True,
-                 device=None, process_group=None):
+                 device=None, process_group=None, deterministic=False):
         if not torch.cuda.is_available():
             raise _lib.EpdeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
@@ -46,7 +46,7 @@ class StepEngine:
         self.eig_w = [float(v) for v in eig_w][: self.k]
         if len(self.eig_w) < self.k:
             raise _lib.EpdeError("only %d weights for %d eigenvalues" % (len(self.eig_w), self.k))
-        self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort)
+        self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort, deterministic)
         self.pg = process_group
         n = C.c_int64()
         _lib.check(self.lib.epde_param_count(C.byref(self.desc), C.byref(n)), "epde_param_count")

@@ -60,6 +60,9 @@ enum {
 };
 
 #define EPDE_FLAG_SORT 1u     /* sort_eigvals_in_training (src/pytorch_eigen_solver.py:217-221) */
+#define EPDE_FLAG_DETERMINISTIC 2u  /* bit-identical gradients run to run: the tensor-core kernels then add tile
+                                     contributions in a fixed order (costs ~7 % of the step); the FFMA2 kernels
+                                     and the generic path always are */
 
 typedef struct epde_desc {
   int32_t d;                            /* input dimension n_0 (data_set.tot_dim) */

@@ -129,3 +129,11 @@ def test_minibatch_edge_cases(L):
     assert (out == 0).all()                          # K = 1: every draw is row 0
     assert L.epde_minibatch_indices(mt, C.byref(pos), 10, 0, out.ctypes.data_as(C.c_void_p)) == 0   # empty batch
     assert L.epde_minibatch_indices(mt, C.byref(pos), 0, 4, out.ctypes.data_as(C.c_void_p)) == -6
+
+
+def test_fused_family_switch(L):
+    """epde_set_fused_impl: 0 = FFMA2 kernels, 1 = tcgen05 kernels (default); anything else is an argument error."""
+    assert L.epde_set_fused_impl(0) == 0
+    assert L.epde_set_fused_impl(1) == 0
+    assert L.epde_set_fused_impl(2) == -6
+    assert L.epde_set_fused_impl(-1) == -6

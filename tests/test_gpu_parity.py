@@ -383,3 +383,51 @@ def test_device_side_averaging_and_eig_stats():
         want_stats[k:] += eig ** 2
     assert np.array_equal(avg.cpu().numpy(), want_avg)          # fp64 sums of fp32 values: exact
     assert np.allclose(stats.cpu().numpy(), want_stats, rtol=1e-15)
+
+
+@pytest.fixture()
+def fused_impl():
+    """Select a kernel family of the fused path for one test and restore the default (tensor cores) afterwards."""
+    from eigenpde_nn_b200 import _lib
+    L = _lib.lib()
+
+    def select(impl):
+        _lib.check(L.epde_set_fused_impl(impl), "epde_set_fused_impl")
+    yield select
+    _lib.check(L.epde_set_fused_impl(1), "epde_set_fused_impl")
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["ffma2", "tcgen05"])
+@pytest.mark.parametrize("shape", [(50, 3, 4099), (2, 2, 2000), (30, 2, 1500), (50, 6, 2500), (7, 1, 300), (60, 3, 900)],
+                         ids=lambda s: "d%d_k%d_B%d" % s)
+def test_both_fused_families_vs_oracle(fused_impl, impl, shape):
+    """The FFMA2 kernels (epde_fused.cuh) and the tcgen05 3xTF32 kernels (epde_tc_fused.cuh / epde_tc_pass2.cuh)
+    compute the same step: both are held to 1e-5 against the fp64 oracle on the BASELINE shapes."""
+    d, k, B = shape
+    fused_impl(impl)
+    c = _rand_case(d * 7 + k, d, k, [20, 20, 20], 3000, B)
+    eng = _engine(c)
+    assert eng.fused
+    _check(c, _oracle(c), eng.step(c["idx"], _flat(c["params"]), c["alpha"]))
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["ffma2", "tcgen05"])
+def test_fused_families_full_size_properties(fused_impl, impl):
+    """B = 2^20 (the bench shape): size-independent properties instead of the oracle -- the loss decomposes into
+    non-penalty + alpha * penalty, eigenvalue estimates are sorted, a second call is bit-identical, and the two
+    families agree with each other to fp32 round-off."""
+    fused_impl(impl)
+    c = _rand_case(77, 50, 3, [20, 20, 20], 1 << 18, 1 << 20)
+    eng = _engine(c, deterministic=True)      # EPDE_FLAG_DETERMINISTIC: fixed accumulation order in the tcgen05 kernels
+    p = _flat(c["params"])
+    r1 = eng.step(c["idx"], p, c["alpha"])
+    g1 = r1["grad"].clone()
+    r2 = eng.step(c["idx"], p, c["alpha"])
+    assert torch.equal(g1, r2["grad"]) and r1["loss"] == r2["loss"]          # bit-identical run to run
+    assert abs(r1["loss"] - (r1["non_penalty"] + c["alpha"] * r1["penalty"])) <= 1e-9 * abs(r1["loss"])
+    assert list(r1["eig_vals"]) == sorted(r1["eig_vals"])
+    fused_impl(1 - impl)
+    eng2 = _engine(c)                         # default flags: free accumulation order (fp32 round-off differences only)
+    r3 = eng2.step(c["idx"], p, c["alpha"])
+    assert abs(r3["loss"] - r1["loss"]) <= 1e-5 * abs(r1["loss"])
+    assert float((r3["grad"] - g1).norm() / g1.norm()) <= 1e-5
