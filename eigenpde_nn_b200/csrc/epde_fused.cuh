@@ -120,6 +120,7 @@ k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t
   srow[t] = v ? r : -1;
   wt[n] = v ? (w ? w[r] : 1.f) : 0.f;
   __syncthreads();
+#pragma unroll 4
   for (int c = t; c < GT * nq; c += 256) {
     const int row = c / nq, q = c - row * nq;
     const int64_t rr = srow[row];
