@@ -21,12 +21,12 @@ FLAG_DETERMINISTIC = 2
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
            "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
-           "epde_eig_stats_accumulate", "epde_set_fused_impl"]
+           "epde_eig_stats_accumulate", "epde_set_fused_impl", "epde_md_align"]
 
 
 class EpdeDesc(C.Structure):
     _fields_ = [("d", C.c_int32), ("d_pad", C.c_int32), ("k", C.c_int32), ("n_layers", C.c_int32),
-                ("widths", C.c_int32 * (EPDE_MAX_LAYERS + 1)), ("act_id", C.c_int32), ("flags", C.c_uint32)]
+                ("widths", C.c_int32 * (EPDE_MAX_LAYERS + 1)), ("act_id", C.c_int32), ("flags", C.c_uint32), ("metric", C.c_void_p)]
 
 
 class EpdeError(RuntimeError):
@@ -62,6 +62,7 @@ def lib():
         L.epde_average_accumulate.argtypes = [dp, vp, vp, vp, vp]
         L.epde_eig_stats_accumulate.argtypes = [dp, vp, vp, vp]
         L.epde_set_fused_impl.argtypes = [C.c_int]
+        L.epde_md_align.argtypes = [i64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp]
         for name in EXPORTS:
             if name != "epde_error_string":
                 getattr(L, name).restype = C.c_int
@@ -74,7 +75,7 @@ def check(rc: int, what: str):
         raise EpdeError("%s failed: %d (%s)" % (what, rc, lib().epde_error_string(rc).decode()))
 
 
-def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False) -> EpdeDesc:
+def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, metric_ptr=None) -> EpdeDesc:
     """arch = [d, n_1, ..., n_{L-1}, 1] (src/pytorch_eigen_solver.py:352)."""
     if len(arch) - 1 > EPDE_MAX_LAYERS:
         raise EpdeError("too many layers")
@@ -85,4 +86,5 @@ def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False) -
     # unknown activation names fall back to CELU in the reference (src/network_arch.py:27-32)
     D.act_id = ACT_IDS.get(activation_name, ACT_IDS["CELU"])
     D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0)
+    D.metric = metric_ptr
     return D

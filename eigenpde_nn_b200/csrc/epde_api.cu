@@ -9,6 +9,7 @@
 #include "epde_fused.cuh"
 #include "epde_generic.cuh"
 #include "epde_tc_api.h"
+#include "epde_md_align.cuh"
 
 using namespace epde;
 
@@ -36,6 +37,7 @@ int check_desc(const epde_desc* D) {
 }
 
 bool fused_ok(const epde_desc* D) {
+  if (D->metric) return false;                  // per-row metric (MD alignment layer): generic family only
   if (D->n_layers != 4 || D->act_id != EPDE_ACT_TANH) return false;
   if (D->widths[1] != kFusedH || D->widths[2] != kFusedH || D->widths[3] != kFusedH) return false;
   if (D->k > 6) return false;
@@ -381,6 +383,21 @@ __global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p,
 __global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict__ out, int k) {
   const int i = threadIdx.x;
   if (i < k) { const double e = out[EPDE_OUT_EIG(k) + i]; stats[i] += e; stats[k + i] += e * e; }
+}
+
+int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* X, const double* ref_x, const int32_t* ref_index,
+                  int32_t m, const float* diag, float* Xa, float* metric, void* stream) {
+  if (!X || !ref_x || !ref_index || !diag || !Xa) return EPDE_ERR_NULL;
+  if (K <= 0 || n_atoms < 1 || n_atoms > MD_MAX_ATOMS || m < 1 || m > MD_MAX_REF || d_pad < 3 * n_atoms) return EPDE_ERR_ARG;
+  MdRef ref;
+  ref.m = m;
+  for (int s = 0; s < m; s++) {
+    if (ref_index[s] < 0 || ref_index[s] >= n_atoms) return EPDE_ERR_ARG;
+    ref.index[s] = ref_index[s];
+    for (int i = 0; i < 3; i++) ref.q[s][i] = ref_x[3 * s + i];
+  }
+  k_md_align<<<(unsigned)K, 64, 0, (cudaStream_t)stream>>>(X, K, n_atoms, d_pad, ref, diag, Xa, metric);
+  return (int)cudaGetLastError();
 }
 
 int epde_set_fused_impl(int impl) {

@@ -128,12 +128,23 @@ __global__ void g_pad_weights(int rows, int cols, int ldp, const float* __restri
   Wp[e] = (c < cols) ? W[(size_t)r * cols + c] : 0.f;
 }
 // e[b] = sum_j c_j U0[b][j]^2 ; y[b] -> ybuf / ebuf columns of net `net`
+// (metric != NULL: e[b] = U0[b]^T M_row U0[b] with the per-row metric of the MD alignment layer, row = idx[b0 + b])
 __global__ void g_energy(int Bc, int d, int ldu, const float* __restrict__ U0, const float* __restrict__ c,
                          const float* __restrict__ ycol, int64_t b0, int k, int net, float* __restrict__ ybuf,
-                         float* __restrict__ ebuf) {
+                         float* __restrict__ ebuf, const float* __restrict__ metric = nullptr,
+                         const int64_t* __restrict__ idx = nullptr) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= Bc) return;
   float s = 0.f;
+  if (metric) {
+    const float* M = metric + (size_t)(idx ? idx[b0 + b] : b0 + b) * d * d;
+    const float* u = U0 + (size_t)b * ldu;
+    for (int i = 0; i < d; i++) {
+      float t = 0.f;
+      for (int j = 0; j < d; j++) t = fmaf(M[i * d + j], u[j], t);
+      s = fmaf(t, u[i], s);
+    }
+  } else
   for (int j = 0; j < d; j++) { const float u = U0[(size_t)b * ldu + j]; s = fmaf(c[j] * u, u, s); }
   ebuf[(b0 + b) * k + net] = s;
   ybuf[(b0 + b) * k + net] = ycol[b];
@@ -174,11 +185,19 @@ __global__ void g_reduce_part(const double* __restrict__ part, int nb, int ns, d
 // Ubar_0 = 2 c (.) U_0 * ebar,  ebar = w_n * ecoef[net]
 __global__ void g_seed(int Bc, int d, int ldu, const float* __restrict__ U0, const float* __restrict__ c,
                        const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t b0,
-                       const Coef* __restrict__ coef, int net, float* __restrict__ Ub) {
+                       const Coef* __restrict__ coef, int net, float* __restrict__ Ub,
+                       const float* __restrict__ metric = nullptr) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)Bc * ldu) return;
   const int b = (int)(e / ldu), j = (int)(e % ldu);
-  const float eb = w[idx ? idx[b0 + b] : b0 + b] * coef->ecoef[net];
+  const int64_t row = idx ? idx[b0 + b] : b0 + b;
+  const float eb = w[row] * coef->ecoef[net];
+  if (metric) {                                              // Ubar_0 = 2 ebar M U_0
+    float t = 0.f;
+    if (j < d) { const float* M = metric + (size_t)row * d * d + (size_t)j * d; for (int i = 0; i < d; i++) t = fmaf(M[i], U0[(size_t)b * ldu + i], t); }
+    Ub[e] = 2.f * t * eb;
+    return;
+  }
   Ub[e] = (j < d) ? 2.f * c[j] * U0[e] * eb : 0.f;          // padding columns stay zero
 }
 // Ubar_l = phi'(Z_l) Gbar_l ; Zbar_l = phi''(Z_l) U_l Gbar_l
@@ -391,7 +410,7 @@ inline int generic_partial(const epde_desc* D, const float* X, const float* w, c
     for (int net = 0; net < D->k; net++) {
       const NetParams np = net_params(P, params, net);
       generic_fwd_jac(D, P, np, Bc, true, st);
-      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, P.Z[P.L], b0, D->k, net, P.ybuf, P.ebuf);
+      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, P.Z[P.L], b0, D->k, net, P.ybuf, P.ebuf, D->metric, idx);
     }
   }
   int nb = (int)((B + 255) / 256); if (nb > 256) nb = 256;
@@ -419,7 +438,7 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
       const NetParams np = net_params(P, params, net);
       generic_fwd_jac(D, P, np, Bc, true, st);
       // ---- first reverse sweep (energy term), l = 1..L
-      g_seed<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, w, idx, b0, P.coef, net, P.Ub);
+      g_seed<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, w, idx, b0, P.coef, net, P.Ub, D->metric);
       for (int l = 1; l <= L; l++) {
         // dW_l += g_l^T ubar_{l-1}
         gemm<true, false>(st, tc, P.n[l], P.w[l - 1], Bc, P.G[l], P.n[l], P.Ub, P.w[l - 1], nullptr, P.n[l - 1], nullptr,

@@ -33,7 +33,7 @@ class StepEngine:
     """
 
     def __init__(self, X, weights, arch, k, activation_name, diag_coeff, beta, eig_w, sort=True,
-                 device=None, process_group=None, deterministic=False):
+                 device=None, process_group=None, deterministic=False, metric=None):
         if not torch.cuda.is_available():
             raise _lib.EpdeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
@@ -46,7 +46,13 @@ class StepEngine:
         self.eig_w = [float(v) for v in eig_w][: self.k]
         if len(self.eig_w) < self.k:
             raise _lib.EpdeError("only %d weights for %d eigenvalues" % (len(self.eig_w), self.k))
-        self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort, deterministic)
+        # per-row metric [K, d, d] of the MD alignment layer (see md_align below); X then holds the ALIGNED rows
+        self.metric = None
+        if metric is not None:
+            self.metric = metric.to(self.device, torch.float32).contiguous()
+            assert self.metric.dim() == 3 and self.metric.shape[1] == self.d and self.metric.shape[2] == self.d
+        self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort, deterministic,
+                                   self.metric.data_ptr() if self.metric is not None else None)
         self.pg = process_group
         n = C.c_int64()
         _lib.check(self.lib.epde_param_count(C.byref(self.desc), C.byref(n)), "epde_param_count")
@@ -175,6 +181,37 @@ class EigenLossFn(torch.autograd.Function):
             outs.append(g[off:off + n].view(shp))
             off += n
         return (None, None, None) + tuple(outs)
+
+
+def md_align(X, ref_x, ref_index, diag_coeff, device=None, want_metric=True):
+    """`MD_data_set.align` (src/data_set.py:126-153) for every row of X on the GPU, once per data set.
+
+    X [K, 3 * n_atoms] raw coordinates (host array / tensor), ref_x [m, 3], ref_index [m] as read by
+    `load_ref_state` (:112-124).  Returns (Xa, metric): the aligned rows as a [K, d_pad] fp32 device tensor
+    (zero padding columns, the layout StepEngine takes as a device mirror) and the per-row metric
+    M = J diag(diag_coeff) J^T [K, d, d] fp32 of the layer's Jacobian (None if want_metric is False)."""
+    if not torch.cuda.is_available():
+        raise _lib.EpdeError("md_align needs a CUDA device (no CPU fallback)")
+    L = _lib.lib()
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    K, d = Xt.shape
+    assert d % 3 == 0
+    d_pad = (d + 3) // 4 * 4
+    with torch.cuda.device(dev):
+        Xd = torch.zeros((K, d_pad), dtype=torch.float32, device=dev)
+        Xd[:, :d] = Xt.to(dev)
+        Xa = torch.zeros_like(Xd)
+        metric = torch.empty((K, d, d), dtype=torch.float32, device=dev) if want_metric else None
+        diag = torch.as_tensor(np.asarray(diag_coeff), dtype=torch.float32).to(dev).contiguous()
+        ref = np.ascontiguousarray(np.asarray(ref_x, dtype=np.float64).reshape(-1, 3))
+        ri = np.ascontiguousarray(np.asarray(ref_index, dtype=np.int32))
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.epde_md_align(C.c_int64(K), C.c_int32(d // 3), C.c_int32(d_pad), _ptr(Xd),
+                                   ref.ctypes.data_as(C.c_void_p), ri.ctypes.data_as(C.c_void_p), C.c_int32(len(ri)),
+                                   _ptr(diag), _ptr(Xa), _ptr(metric), st), "epde_md_align")
+        torch.cuda.synchronize(dev)
+    return Xa, metric
 
 
 class DeviceTrainer:

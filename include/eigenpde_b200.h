@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define EPDE_ABI_VERSION 1
+#define EPDE_ABI_VERSION 2      /* 2: epde_desc.metric, epde_md_align */
 #define EPDE_MAX_LAYERS 8   /* Linear layers per net */
 #define EPDE_MAX_K 8        /* eigenfunctions (nets) */
 
@@ -72,6 +72,10 @@ typedef struct epde_desc {
   int32_t widths[EPDE_MAX_LAYERS + 1];  /* n_0 .. n_L, n_L must be 1 (src/pytorch_eigen_solver.py:352) */
   int32_t act_id;                       /* EPDE_ACT_* */
   uint32_t flags;                       /* EPDE_FLAG_* */
+  const float* metric;                  /* NULL, or device pointer to a per-ROW symmetric metric [K][d][d] that replaces
+                                           diag(diag_coeff) in the energy: e = grad f^T M grad f.  Used for the MD
+                                           alignment layer (src/data_set.py:126-160): X then holds the ALIGNED rows and
+                                           metric the J diag(c) J^T written by epde_md_align */
 } epde_desc;
 
 /* out_scalars layout (fp64, device): what update_step returns at :236 plus the moments */
@@ -175,6 +179,18 @@ int epde_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float
 int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d_params,
                             const double* d_out_scalars, void* stream);
 int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
+
+/*
+ * MD pre-processing layer `MD_data_set.align` (src/data_set.py:126-153; called from every net's forward,
+ * src/network_arch.py:62): Kabsch alignment of each configuration (n_atoms x 3 coordinates per row of d_X) to the
+ * reference configuration ref_x[m][3] over the atoms ref_index[m] (file format: load_ref_state :112-124).
+ * The layer has no parameters, so it is evaluated once per data set: d_Xa receives the aligned rows (same layout
+ * as d_X) and d_metric, if not NULL, the per-row metric M = J diag(d_diag) J^T [K][d][d] of the layer's Jacobian,
+ * with which the step reproduces the reference's input gradients through the layer (epde_desc.metric).
+ * ref_x / ref_index are HOST arrays; m <= 21, n_atoms <= 21.
+ */
+int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* d_X, const double* ref_x,
+                  const int32_t* ref_index, int32_t m, const float* d_diag, float* d_Xa, float* d_metric, void* stream);
 
 /*
  * Kernel family of the fused path (reference architecture d -> 20 -> 20 -> 20 -> 1, Tanh):

@@ -162,7 +162,7 @@ def coefficients(W, S1, S2, E, beta, alpha, eig_w, sort=True):
 
 
 def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=True, global_sums=None,
-         sums_only=False):
+         sums_only=False, metric=None):
     """Loss, eigenvalue estimates and parameter gradients for one batch.
 
     x [B,d] fp64 (already gathered), w [B] fp64.
@@ -170,6 +170,8 @@ def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=T
     global_sums=(W,S1,S2,E): use these batch-global sums instead of the local ones (the samples
     given are then one shard of the batch and `grads` is that shard's additive share).
     sums_only: stop after the local sums (phase 1 of a sharded step).
+    metric [B,d,d] (symmetric): per-sample metric replacing diag(c) in the energy, e = u0^T M u0 - the MD alignment
+    layer (oracle/md_align.py: x is then the ALIGNED minibatch and M = J diag(c) J^T).
     """
     act = ACTIVATIONS[activation]
     x = np.asarray(x, dtype=np.float64)
@@ -183,7 +185,11 @@ def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=T
         g, u = input_jacobian(layers, cache)
         ys.append(y); caches.append(cache); gs.append(g); us.append(u)
     y = np.stack(ys, axis=1)
-    e = np.stack([(c[None, :] * u[0] ** 2).sum(axis=1) for u in us], axis=1)
+    if metric is None:
+        mu0 = [c[None, :] * u[0] for u in us]                       # M u0 with M = diag(c)
+    else:
+        mu0 = [np.einsum("bij,bj->bi", np.asarray(metric, np.float64), u[0]) for u in us]
+    e = np.stack([(m_ * u[0]).sum(axis=1) for m_, u in zip(mu0, us)], axis=1)
     W, S1, S2, E = batch_sums(y, e, w)
     if sums_only:
         return dict(sums=dict(W=W, S1=S1, S2=S2, E=E), y=y, e=e)
@@ -200,7 +206,7 @@ def step(params, x, w, diag_coeff, beta, alpha, eig_w, activation="Tanh", sort=T
         gW = [np.zeros_like(Wl) for Wl, _ in layers]
         gb = [np.zeros_like(bl) for _, bl in layers]
         zbar = [None] * (L + 1)
-        ubar = 2.0 * c[None, :] * u[0] * ebar[:, None]            # ubar_0
+        ubar = 2.0 * mu0[i] * ebar[:, None]                         # ubar_0 = 2 ebar M u0
         for l in range(1, L + 1):
             gW[l - 1] += g[l].T @ ubar
             gbar = ubar @ layers[l - 1][0].T                       # W_l ubar_{l-1}

@@ -79,6 +79,10 @@ CASES = [
     dict(name="cfg3_md_30d_k2", d=30, k=2, arch=[20, 20, 20], act="Tanh", K=3000, B=1000, data="md30",
          weights="heavy", beta=1.0 / (0.001987191 * 300.0), alpha=20.0, eig_w=[1.0, 0.8], md=True,
          diffusion_coeff=1e-5, seed=14),
+    # MD mode WITH the Kabsch alignment layer (src/data_set.py:126-160) inside every net's forward
+    dict(name="cfg3_md_30d_k2_aligned", d=30, k=2, arch=[20, 20, 20], act="Tanh", K=1200, B=500, data="md30",
+         weights="heavy", beta=1.0 / (0.001987191 * 300.0), alpha=20.0, eig_w=[1.0, 0.8], md=True,
+         diffusion_coeff=1e-5, seed=24, align=True, ref_index=[0, 2, 5, 7, 8]),
     dict(name="cfg4_50d_k6", d=50, k=6, arch=[20, 20, 20], act="Tanh", K=1500, B=1024, data="ring50",
          weights="lognormal", beta=1.0, alpha=20.0, eig_w=[1.0, 0.8, 0.6, 0.3, 0.2, 0.1], md=False, seed=15),
     dict(name="cfg5_wide128_50d_k4", d=50, k=4, arch=[128, 128, 128, 128], act="Tanh", K=600, B=192, data="ring50",
@@ -137,6 +141,16 @@ def run_case(pes, na, ds, case):
     X, w = synth_data(case, rng)
     with tempfile.TemporaryDirectory() as wd:
         solver = make_solver(pes, na, ds, case, X, w, wd)
+    extra = {}
+    if case.get("align"):                           # MD_data_set + reference configuration, as `run` does (:343-346)
+        solver.dataset = ds.MD_data_set(X, w)
+        ri = list(case["ref_index"])
+        ref = X[0].reshape(-1, 3)[ri]
+        ref = (ref - ref.mean(axis=0, keepdims=True)).astype(np.float32).astype(np.float64)
+        solver.dataset.ref_num_atoms = len(ri)
+        solver.dataset.ref_index = ri
+        solver.dataset.ref_x = torch.from_numpy(ref).double()
+        extra = dict(ref_x=ref, ref_index=np.asarray(ri, np.int64))
     random.seed(case["seed"] + 1000)
     eig, cvec, loss, nonpen, pen = solver.update_step(case["B"], case["alpha"])
     idx = np.asarray(solver.dataset.active_indices, dtype=np.int64)
@@ -146,7 +160,10 @@ def run_case(pes, na, ds, case):
                diag_coeff=solver.diag_coeff.numpy().copy(), beta=np.float64(solver.beta),
                alpha=np.float64(case["alpha"]), eig_w=np.asarray(case["eig_w"], np.float64),
                k=np.int64(case["k"]), act=np.str_(case["act"]), minibatch_seed=np.int64(case["seed"] + 1000),
-               arch=np.asarray([X.shape[1]] + list(case["arch"]) + [1], np.int64))
+               arch=np.asarray([X.shape[1]] + list(case["arch"]) + [1], np.int64), **extra)
+    if case.get("align"):                           # the aligned minibatch the nets saw (for the oracle's own check)
+        with torch.no_grad():
+            out["x_aligned"] = solver.dataset.align().numpy().copy()
     for i, net in enumerate(solver.model.nets):
         for l, lin in enumerate(net.linears):
             out[f"W_{i}_{l}"] = lin.weight.detach().numpy().astype(np.float32)
@@ -211,12 +228,17 @@ def dropin_run(pes):
 def main():
     pes, na, ds = import_reference()
     os.makedirs(OUT, exist_ok=True)
+    only = os.environ.get("EPDE_GOLDEN_ONLY")      # regenerate a single fixture without touching the others
     for case in CASES:
+        if only and case["name"] != only:
+            continue
         out = run_case(pes, na, ds, case)
         path = os.path.join(OUT, case["name"] + ".npz")
         np.savez_compressed(path, **out)
         print("%-28s loss=%.6f eig=%s cvec=%s  %.0f KB" % (case["name"], out["loss"], np.round(out["eig_vals"], 4),
                                                          out["cvec"], os.path.getsize(path) / 1024))
+    if only:
+        return
     np.savez_compressed(os.path.join(OUT, "index_streams.npz"), **index_streams())
     print("index streams written")
     np.savez_compressed(os.path.join(OUT, "dropin_run.npz"), **dropin_run(pes))

@@ -15,8 +15,11 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+MD_ALIGNED = "cfg3_md_30d_k2_aligned"       # MD mode with the Kabsch alignment layer in the forward: its own tests
+
+
 def golden_names():
-    skip = {"index_streams.npz", "dropin_run.npz"}
+    skip = {"index_streams.npz", "dropin_run.npz", MD_ALIGNED + ".npz"}
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in skip)
 
 
@@ -30,7 +33,11 @@ def load_golden(name):
               for i in range(k)]
     grads = [[(z[f"gW_{i}_{l}"].astype(np.float64), z[f"gb_{i}_{l}"].astype(np.float64)) for l in range(L)]
              for i in range(k)]
-    return dict(name=name, k=k, arch=arch, act=str(z["act"]), X=z["X"].astype(np.float64), w=z["w"].astype(np.float64),
+    extra = {}
+    if "ref_x" in z.files:                       # MD-aligned fixture: reference configuration + the aligned minibatch
+        extra = dict(ref_x=z["ref_x"].astype(np.float64), ref_index=[int(v) for v in z["ref_index"]],
+                     x_aligned=z["x_aligned"].astype(np.float64))
+    return dict(**extra, name=name, k=k, arch=arch, act=str(z["act"]), X=z["X"].astype(np.float64), w=z["w"].astype(np.float64),
                 idx=z["idx"], params=params, grads=grads, eig_vals=z["eig_vals"], cvec=z["cvec"],
                 loss=float(z["loss"]), non_penalty=float(z["non_penalty"]), penalty=float(z["penalty"]),
                 diag_coeff=z["diag_coeff"], beta=float(z["beta"]), alpha=float(z["alpha"]),

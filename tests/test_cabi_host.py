@@ -26,7 +26,7 @@ def test_exports_match_header(L):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.epde_abi_version() == 1
+    assert L.epde_abi_version() == 2
     assert L.epde_error_string(0) == b"ok"
     assert b"workspace" in L.epde_error_string(-4)
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import check_step_against, golden_names, load_golden, unflatten
+from conftest import MD_ALIGNED, check_step_against, golden_names, load_golden, unflatten
 from oracle import closed_form
 
 pytestmark = pytest.mark.gpu
@@ -431,3 +431,25 @@ def test_fused_families_full_size_properties(fused_impl, impl):
     r3 = eng2.step(c["idx"], p, c["alpha"])
     assert abs(r3["loss"] - r1["loss"]) <= 1e-5 * abs(r1["loss"])
     assert float((r3["grad"] - g1).norm() / g1.norm()) <= 1e-5
+
+
+def test_md_align_kernel_and_metric_step_vs_reference():
+    """SURVEY 8(f) N1 on the GPU: `epde_md_align` (aligned rows + per-row metric of the alignment Jacobian) against the
+    oracle, then the step with `epde_desc.metric` against the outputs of the unmodified reference run in MD mode
+    (alignment layer inside every net's forward)."""
+    from eigenpde_nn_b200.engine import StepEngine, md_align as gpu_md_align
+    from oracle import md_align
+    g = load_golden(MD_ALIGNED)
+    Xa, M = gpu_md_align(g["X"], g["ref_x"], g["ref_index"], g["diag_coeff"])
+    d = g["arch"][0]
+    rows = g["idx"][:64]
+    xa_ref, M_ref = md_align.align_batch(g["X"][rows], g["ref_x"], g["ref_index"], g["diag_coeff"])
+    assert np.abs(Xa[rows, :d].cpu().numpy() - xa_ref).max() <= 2e-6 * np.abs(xa_ref).max()       # fp32 storage
+    assert np.abs(M[rows].cpu().numpy() - M_ref).max() <= 2e-6 * np.abs(M_ref).max()
+    assert float(Xa[:, d:].abs().max()) == 0.0                                                       # padding columns
+    eng = StepEngine(Xa, torch.from_numpy(g["w"]), g["arch"], g["k"], g["act"], g["diag_coeff"], g["beta"], g["eig_w"],
+                     metric=M)
+    assert not eng.fused                        # per-row metric: generic family
+    res = eng.step(g["idx"], _flat(g["params"]), g["alpha"])
+    grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), g["arch"], g["k"])
+    check_step_against(g, res, TOL, grads)

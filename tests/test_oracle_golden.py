@@ -5,8 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, check_step_against, golden_names, load_golden
-from oracle import closed_form, minibatch, ref_port
+from conftest import GOLDEN, MD_ALIGNED, check_step_against, golden_names, load_golden
+from oracle import closed_form, md_align, minibatch, ref_port
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -54,3 +54,39 @@ def test_minibatch_matches_cpython_random_live():
         random.seed(seed)
         ref = random.choices(range(K), cum_weights=np.arange(1, K + 1), k=B)
         assert np.array_equal(minibatch.MT19937(seed).minibatch(K, B), np.asarray(ref))
+
+
+def test_md_alignment_layer_matches_reference():
+    """the reference run with `MD_data_set` + reference configuration (alignment inside every net's
+    forward, differentiated by autograd) against the oracle's restatement: aligned rows, closed-form Jacobian, and the
+    whole step with the per-sample metric M = J diag(c) J^T."""
+    g = load_golden(MD_ALIGNED)
+    xb, wb = g["X"][g["idx"]], g["w"][g["idx"]]
+    xa, M = md_align.align_batch(xb, g["ref_x"], g["ref_index"], g["diag_coeff"])
+    assert np.abs(xa - g["x_aligned"]).max() <= 1e-12
+    out = closed_form.step(g["params"], xa, wb, g["diag_coeff"], g["beta"], g["alpha"], g["eig_w"], g["act"], metric=M)
+    check_step_against(g, out, 1e-9, out["grads"])
+
+
+def test_md_alignment_jacobian_matches_autograd():
+    """The closed-form derivative of the Kabsch rotation (no autograd) against torch.autograd on the reference's
+    SVD expression (src/data_set.py:133-153)."""
+    g = load_golden(MD_ALIGNED)
+    ref, ri = torch.from_numpy(g["ref_x"]), g["ref_index"]
+
+    def align_like_reference(x):
+        p = x.reshape(-1, 3)
+        sel = p[ri]
+        c = sel.mean(0, keepdim=True)
+        H = (sel - c).T @ ref
+        u, s, vh = torch.linalg.svd(H)
+        D = torch.eye(3, dtype=torch.float64)
+        D[2, 2] = torch.sign(torch.linalg.det(u @ vh)).detach()
+        return ((p - c) @ (u @ D @ vh)).reshape(-1)
+
+    for n in (0, 7, 123):
+        x = g["X"][g["idx"][n]]
+        Jt = torch.autograd.functional.jacobian(align_like_reference, torch.from_numpy(x)).numpy()
+        xa, J = md_align.align_one(x, g["ref_x"], ri)
+        assert np.abs(J - Jt).max() <= 1e-12
+        assert np.abs(xa - align_like_reference(torch.from_numpy(x)).numpy()).max() <= 1e-12
