@@ -73,8 +73,10 @@ class data_set():
 
 class MD_data_set(data_set):
     """Molecular data: states aligned to a reference configuration before entering the nets
-    (reference: data_set.py:91-160).  Kept for the loaders / evaluation scripts; training with the
-    alignment layer on the B200 path is a "next" row."""
+    (reference: data_set.py:91-160).  `align` / `pre_processing_layer` keep the reference's minibatch semantics for
+    the loaders and evaluation scripts; for training, `eigen_solver.run` evaluates the (parameter-free) layer once
+    for the whole data set on the GPU (`engine.md_align` -> `epde_md_align`: aligned rows + the metric of the layer's
+    Jacobian), SURVEY.md 8(f) N1."""
 
     def __init__(self, xvec, weights):
         super().__init__(xvec, weights)

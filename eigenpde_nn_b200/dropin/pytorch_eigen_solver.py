@@ -257,11 +257,6 @@ class eigen_solver():
         if self.md_data_flag:
             self.dataset = data_set.MD_data_set.from_file(states_filename)
             self.dataset.load_ref_state()
-            if os.environ.get("EPDE_MD_NO_ALIGN") != "1":
-                raise NotImplementedError(
-                    "md_data_flag=True uses the Kabsch alignment pre-processing layer (src/data_set.py:126-160), "
-                    "which the B200 step does not implement yet (SURVEY.md 8(f) N1). Set EPDE_MD_NO_ALIGN=1 to train "
-                    "on the raw coordinates.")
         else:
             self.dataset = data_set.data_set.from_file(states_filename)
 
@@ -282,9 +277,20 @@ class eigen_solver():
         self.averaged_model.double()
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.learning_rate_list[0])
 
-        self.engine = StepEngine(self.dataset.X_vec.numpy(), self.dataset.weights.numpy(), self.arch_list, self.k,
-                                 self.activation_name, self.diag_coeff.numpy(), self.beta, self.eig_w,
-                                 sort=self.sort_eigvals_in_training)
+        if self.md_data_flag and os.environ.get("EPDE_MD_NO_ALIGN") != "1":
+            # The alignment layer (src/data_set.py:126-160, inside every net's forward in the reference) has no
+            # parameters: it is evaluated ONCE for the whole data set; the step then runs on the aligned rows with the
+            # per-row metric of the layer's Jacobian, which reproduces the reference's input gradients exactly.
+            from eigenpde_nn_b200.engine import md_align
+            Xa, metric = md_align(self.dataset.X_vec.numpy(), self.dataset.ref_x.numpy(), self.dataset.ref_index,
+                                  self.diag_coeff.numpy())
+            self.engine = StepEngine(Xa, self.dataset.weights, self.arch_list, self.k, self.activation_name,
+                                     self.diag_coeff.numpy(), self.beta, self.eig_w,
+                                     sort=self.sort_eigvals_in_training, metric=metric)
+        else:
+            self.engine = StepEngine(self.dataset.X_vec.numpy(), self.dataset.weights.numpy(), self.arch_list, self.k,
+                                     self.activation_name, self.diag_coeff.numpy(), self.beta, self.eig_w,
+                                     sort=self.sort_eigvals_in_training)
 
         tot_num_parameters = sum(p.numel() for p in self.model.parameters())
         print('\n[Info] Time spent for loading data: %.2f Sec' % (time.process_time() - self.start_time))

@@ -225,6 +225,49 @@ def dropin_run(pes):
     return dict(X=X, w=w, seed=np.int64(seed), log=np.str_(log), **{"ck_" + k: v for k, v in ck.items()})
 
 
+def dropin_run_md(pes):
+    """The same for MD mode (`md_data_flag=True`): `run` builds an `MD_data_set`, reads ./data/ref_state.txt and the
+    Kabsch alignment layer sits inside every net's forward, also in the stage-end full-data passes."""
+    import torch
+    rng = np.random.default_rng(77)
+    case = dict(K=900, d=30, data="md30", weights="lognormal")
+    X, w = synth_data(case, rng)
+    X, w = np.round(X, 10), np.round(w, 10)
+    ri = [0, 2, 5, 7, 8]
+    ref = X[0].reshape(-1, 3)[ri]
+    ref = np.round(ref - ref.mean(axis=0, keepdims=True), 8)
+    seed = 2468
+    md_beta = 1.0 / (0.001987191 * 300.0)
+    P = types.SimpleNamespace(
+        k=2, eig_w=[1.0, 0.8], md_data_flag=True, md_beta=md_beta, beta=md_beta, diffusion_coeff=1e-5,
+        stage_list=[0, 4, 8], batch_size_list=[300, 400], sort_eigvals_in_training=True,
+        learning_rate_list=[5e-3, 2e-3], alpha_list=[20.0, 10.0], inner_arch_size_list=[20, 20, 20],
+        activation_name="Tanh", train_max_step=8, load_init_model=False, init_model_name="x.pt",
+        print_every_step=1, data_filename_prefix="states", eig_file_name_prefix="eig", log_filename="log.txt")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as wd:
+        os.makedirs(os.path.join(wd, "data"))
+        with open(os.path.join(wd, "data", "states.txt"), "w") as f:
+            f.write("%d %d\n" % X.shape)
+            np.savetxt(f, np.concatenate([X, w[:, None]], axis=1), fmt="%.10f")
+        with open(os.path.join(wd, "data", "ref_state.txt"), "w") as f:
+            f.write("%d\n%s\n" % (len(ri), " ".join(str(i) for i in ri)))
+            np.savetxt(f, ref, fmt="%.8f")
+        os.chdir(wd)
+        try:
+            solver = pes.eigen_solver(P, seed)
+            solver.run()
+            log = open(os.path.join(wd, "data", "log.txt")).read()
+            ck = {}
+            for name in ["eig", "eig_averaged", "eig_stage1", "eig_stage2_averaged"]:
+                m = torch.load(os.path.join(wd, "data", name + ".pt"), weights_only=False)
+                ck[name] = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).numpy()
+        finally:
+            os.chdir(cwd)
+    return dict(X=X, w=w, seed=np.int64(seed), log=np.str_(log), ref_x=ref, ref_index=np.asarray(ri, np.int64),
+                md_beta=np.float64(md_beta), **{"ck_" + k: v for k, v in ck.items()})
+
+
 def main():
     pes, na, ds = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -237,6 +280,9 @@ def main():
         np.savez_compressed(path, **out)
         print("%-28s loss=%.6f eig=%s cvec=%s  %.0f KB" % (case["name"], out["loss"], np.round(out["eig_vals"], 4),
                                                          out["cvec"], os.path.getsize(path) / 1024))
+    if only == "dropin_run_md" or not only:
+        np.savez_compressed(os.path.join(OUT, "dropin_run_md.npz"), **dropin_run_md(pes))
+        print("MD-mode drop-in run written")
     if only:
         return
     np.savez_compressed(os.path.join(OUT, "index_streams.npz"), **index_streams())

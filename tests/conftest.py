@@ -19,7 +19,7 @@ MD_ALIGNED = "cfg3_md_30d_k2_aligned"       # MD mode with the Kabsch alignment 
 
 
 def golden_names():
-    skip = {"index_streams.npz", "dropin_run.npz", MD_ALIGNED + ".npz"}
+    skip = {"index_streams.npz", "dropin_run.npz", "dropin_run_md.npz", MD_ALIGNED + ".npz"}
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in skip)
 
 

@@ -138,3 +138,44 @@ def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch, devic
         want = z["ck_" + name]
         assert flat.dtype == np.float64 and flat.shape == want.shape
         assert np.linalg.norm(flat - want) / np.linalg.norm(want) < 1e-4, name
+
+
+@pytest.mark.gpu
+def test_md_mode_training_run_matches_reference_log(dropin, tmp_path, monkeypatch):
+    """`md_data_flag=True`: the reference builds an `MD_data_set`, reads ./data/ref_state.txt and runs
+    the Kabsch alignment layer inside every net's forward (training steps AND the stage-end full-data passes).  The
+    drop-in evaluates the layer once per data set on the GPU (`epde_md_align`) and trains on the aligned rows with the
+    per-row Jacobian metric: 8 Adam steps over two stages against the log and checkpoints of the unmodified reference."""
+    monkeypatch.delenv("EPDE_DEVICE_LOOP", raising=False)
+    monkeypatch.delenv("EPDE_MD_NO_ALIGN", raising=False)
+    z = np.load(os.path.join(GOLDEN, "dropin_run_md.npz"))
+    (tmp_path / "data").mkdir()
+    with open(tmp_path / "data" / "states.txt", "w") as fh:
+        fh.write("%d %d\n" % z["X"].shape)
+        np.savetxt(fh, np.concatenate([z["X"], z["w"][:, None]], axis=1), fmt="%.10f")
+    with open(tmp_path / "data" / "ref_state.txt", "w") as fh:
+        fh.write("%d\n%s\n" % (len(z["ref_index"]), " ".join(str(int(i)) for i in z["ref_index"])))
+        np.savetxt(fh, z["ref_x"], fmt="%.8f")
+    monkeypatch.chdir(tmp_path)
+    md_beta = float(z["md_beta"])
+    P = types.SimpleNamespace(
+        k=2, eig_w=[1.0, 0.8], md_data_flag=True, md_beta=md_beta, beta=md_beta, diffusion_coeff=1e-5,
+        stage_list=[0, 4, 8], batch_size_list=[300, 400], sort_eigvals_in_training=True,
+        learning_rate_list=[5e-3, 2e-3], alpha_list=[20.0, 10.0], inner_arch_size_list=[20, 20, 20],
+        activation_name="Tanh", train_max_step=8, load_init_model=False, init_model_name="x.pt",
+        print_every_step=1, data_filename_prefix="states", eig_file_name_prefix="eig", log_filename="log.txt")
+    solver = dropin.pes.eigen_solver(P, int(z["seed"]))
+    solver.run()
+    assert solver.engine.metric is not None and not solver.engine.fused
+    ref = np.array([[float(v) for v in line.split()] for line in str(z["log"]).strip().splitlines()])
+    got = np.loadtxt(tmp_path / "data" / "log.txt", ndmin=2)
+    assert got.shape == ref.shape == (8, 6)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    scale = np.maximum(np.abs(ref[:, 1:]), 1e-2 * np.abs(ref[:, 1:2]))
+    assert (np.abs(got[:, 1:] - ref[:, 1:]) / scale).max() < 2e-4
+    for name in ["eig", "eig_averaged", "eig_stage1", "eig_stage2_averaged"]:
+        m = torch.load(tmp_path / "data" / (name + ".pt"), weights_only=False)
+        flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).numpy()
+        want = z["ck_" + name]
+        assert flat.shape == want.shape
+        assert np.linalg.norm(flat - want) / np.linalg.norm(want) < 1e-4, name
