@@ -17,6 +17,9 @@ namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
 constexpr int kFusedH = 20;
+// family used by the last epde_step_partial on a workspace: epde_step_finish on the same workspace follows it even if
+// epde_set_fused_impl was called in between (the two phases share workspace layouts)
+struct { const void* ws; int impl; } g_last_partial = {nullptr, 1};
 int g_fused_impl = 1;                  // 1: tcgen05 kernels (epde_tc_fused.cuh, default)   0: FFMA2 kernels (epde_fused.cuh)
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
@@ -117,18 +120,17 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
                   const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
-  if (g_fused_impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
-  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, g_fused_impl == 1);
+  const int impl = g_fused_impl;
+  g_last_partial.ws = ws; g_last_partial.impl = impl;
+  if (impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
+  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1);
   if (e != cudaSuccess) return (int)e;
-  if (g_fused_impl == 1)
+  if (impl == 1)
     return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums, st);
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
   const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
-#ifdef EPDE_DEV_ONLY_K3
-  e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part);
-#else
   switch (D->k) {
     case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
     case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
@@ -137,7 +139,6 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
     case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
     default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
   }
-#endif
   if (e != cudaSuccess) return (int)e;
   k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums);
   return (int)cudaGetLastError();
@@ -149,7 +150,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
-  if (g_fused_impl == 1) {
+  if ((g_last_partial.ws == ws ? g_last_partial.impl : g_fused_impl) == 1) {
     int gx = 0;
     rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx,
                     (D->flags & EPDE_FLAG_DETERMINISTIC) ? 1 : 0, st);

@@ -43,8 +43,6 @@ __device__ __forceinline__ void stage_val(uint32_t img_hi, int r, float v) {
   sts32(img_hi + o, hi); sts32(img_hi + SG_IMG + o, lo);
 }
 
-__device__ __forceinline__ void accadd(float* p, float v) { *p += v; }
-
 // one gradient round: D[64 x N] = sum over 128 samples, 3xTF32, small terms first; fresh accumulator
 template <int N>
 __device__ __forceinline__ void issue_round(uint32_t d_t, uint32_t sg_base) {
