@@ -268,13 +268,17 @@ def main():
     # ---- end to end through the host-facing API --------------------------------------------
     out_pin = torch.empty(eng.out.numel(), dtype=torch.float64).pin_memory()
     grad_pin = torch.empty(eng.n_params, dtype=torch.float32).pin_memory()
-    idx_stage = torch.empty(B, dtype=torch.int64, device=dev)
     par_stage = torch.empty_like(params)
+    from eigenpde_nn_b200.engine import MinibatchPipeline
+    pipe = MinibatchPipeline(B, dev)                                   # H2D of step i+1's indices runs behind step i
+    pipe.prefetch(idx_pin[0])
 
     def e2e_step(i):
-        idx_stage.copy_(idx_pin[i % nbatch], non_blocking=True)       # H2D: this step's minibatch indices
+        idx_stage = pipe.acquire()                                     # H2D (copy stream): this step's minibatch indices
         par_stage.copy_(params_h, non_blocking=True)                   # H2D: current parameters
         o, gr = eng.step_device(idx_stage, B, par_stage, ALPHA)
+        pipe.release()
+        pipe.prefetch(idx_pin[(i + 1) % nbatch])                       # next step's indices, every step, 8 B per sample
         out_pin.copy_(o, non_blocking=True)                            # D2H: loss / eigenvalues / penalty
         grad_pin.copy_(gr, non_blocking=True)                          # D2H: gradient for the host optimiser
         torch.cuda.current_stream().synchronize()                      # update_step returns host values (:236)

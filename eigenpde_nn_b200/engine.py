@@ -183,6 +183,44 @@ class EigenLossFn(torch.autograd.Function):
         return (None, None, None) + tuple(outs)
 
 
+class MinibatchPipeline:
+    """Double-buffered host -> device staging of minibatch index arrays on a copy stream.
+
+    The indices of step i+1 do not depend on the result of step i (the reference draws them from the Python RNG,
+    src/data_set.py:67), so their upload can run behind the kernels of step i:
+        pipe.prefetch(idx_pinned_0)
+        for i in ...:  idx_dev = pipe.acquire(); engine.step_device(idx_dev, B, params, alpha); pipe.release();
+                       pipe.prefetch(idx_pinned_{i+1}); ... read results ..."""
+
+    def __init__(self, B, device):
+        self.dev = torch.device(device)
+        self.buf = [torch.empty(B, dtype=torch.int64, device=self.dev) for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(self.dev))
+        self.head = 0          # next buffer to fill
+        self.tail = 0          # next buffer to consume
+
+    def prefetch(self, idx_pinned):
+        b = self.head & 1
+        self.stream.wait_event(self.free[b])
+        with torch.cuda.stream(self.stream):
+            self.buf[b].copy_(idx_pinned, non_blocking=True)
+            self.ready[b].record(self.stream)
+        self.head += 1
+
+    def acquire(self):
+        b = self.tail & 1
+        torch.cuda.current_stream(self.dev).wait_event(self.ready[b])
+        return self.buf[b]
+
+    def release(self):
+        self.free[self.tail & 1].record(torch.cuda.current_stream(self.dev))
+        self.tail += 1
+
+
 def md_align(X, ref_x, ref_index, diag_coeff, device=None, want_metric=True):
     """`MD_data_set.align` (src/data_set.py:126-153) for every row of X on the GPU, once per data set.
 
