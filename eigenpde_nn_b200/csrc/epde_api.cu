@@ -371,6 +371,35 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// The whole per-step epilogue of `train` (:277-284) in ONE launch whose arguments never change, so that a step can be
+// replayed as a CUDA graph: Adam with the hyper-parameters read from device memory (state[0] = lr, state[1] = number
+// of optimiser steps taken so far, incremented here), then averaged_model.nets[i] += model.nets[cvec[i]] with the
+// UPDATED parameters, then the running sums of the sorted eigenvalue estimates.  One CTA (the parameter vector is a
+// few thousand floats): the averaging reads other nets' parameters, so it has to follow a CTA-wide barrier.
+__global__ void __launch_bounds__(1024)
+k_epilogue(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+           double* __restrict__ state, double* __restrict__ avg, double* __restrict__ stats,
+           const double* __restrict__ out, int k) {
+  const double lr = state[0], step = state[1] + 1.0;
+  const float bc1 = (float)(1.0 - pow(0.9, step)), bc2s = (float)sqrt(1.0 - pow(0.999, step));
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gi = g[i];
+    const float mi = 0.9f * m[i] + 0.1f * gi;
+    const float vi = 0.999f * v[i] + 0.001f * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= ((float)lr / bc1) * (mi / (sqrtf(vi) / bc2s + 1e-8f));
+  }
+  __syncthreads();
+  const int64_t per = n / k;
+  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = (int)(e / per);
+    const int src = (int)out[EPDE_OUT_CVEC(k) + i];
+    avg[e] += (double)p[(int64_t)src * per + (e - (int64_t)i * per)];
+  }
+  if (threadIdx.x < k) { const double ev = out[EPDE_OUT_EIG(k) + threadIdx.x]; stats[threadIdx.x] += ev; stats[k + threadIdx.x] += ev * ev; }
+  if (threadIdx.x == 0) state[1] = step;
+}
+
 // averaged_model.nets[i] += model.nets[cvec[i]]  (record_model_parameters, src/pytorch_eigen_solver.py:114-118)
 __global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p, const double* __restrict__ out,
                           int k, int64_t per) {
@@ -405,6 +434,14 @@ int epde_set_fused_impl(int impl) {
   if (impl != 0 && impl != 1) return EPDE_ERR_ARG;
   g_fused_impl = impl;
   return EPDE_OK;
+}
+
+int epde_train_epilogue(const epde_desc* D, float* params, const float* grad, float* m, float* v, double* state,
+                        double* avg, double* stats, const double* out, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!params || !grad || !m || !v || !state || !avg || !stats || !out) return EPDE_ERR_NULL;
+  k_epilogue<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, m, v, param_count(D), state, avg, stats, out, D->k);
+  return (int)cudaGetLastError();
 }
 
 int epde_average_accumulate(const epde_desc* D, double* avg, const float* params, const double* out, void* stream) {

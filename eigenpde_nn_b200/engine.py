@@ -259,7 +259,7 @@ class DeviceTrainer:
     draws the minibatch indices and enqueues.  Nothing is synchronised until `read_scalars()` /
     `download()` is called (every print_every_step / at a stage end)."""
 
-    def __init__(self, engine: StepEngine, model):
+    def __init__(self, engine: StepEngine, model, use_graph=None):
         self.e = engine
         dev = engine.device
         self.p = engine.flat_params(model)
@@ -267,32 +267,71 @@ class DeviceTrainer:
         self.v = torch.zeros_like(self.p)
         self.avg = torch.zeros(engine.n_params, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(2 * engine.k, dtype=torch.float64, device=dev)
-        self.t = 0                       # Adam step count (never reset: the reference keeps one optimiser, :379)
+        # [learning rate, optimiser steps taken so far] in device memory: the step's launches then have constant
+        # arguments and the whole step is replayed as ONE CUDA graph (the optimiser is never reset, :379)
+        self.state = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._lr = None
         self.steps_in_stage = 0
         self._idx_dev = None
+        self._pin, self._pin_ev, self._pin_i = [], [], 0
+        if use_graph is None:
+            import os
+            use_graph = os.environ.get("EPDE_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph) and engine.pg is None      # the multi-rank step runs NCCL between the phases
+        self._graph, self._graph_key, self._seen_key = None, None, None
 
     def start_stage(self):
         self.avg.zero_()
         self.stats.zero_()
         self.steps_in_stage = 0
 
+    def _launch(self, B, alpha):
+        e = self.e
+        out, grad = e.step_device(self._idx_dev, B, self.p, alpha)
+        st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
+        # Adam, then the averaging with the UPDATED parameters (:277, :284), then the eigenvalue running sums
+        _lib.check(e.lib.epde_train_epilogue(C.byref(e.desc), _ptr(self.p), _ptr(grad), _ptr(self.m), _ptr(self.v),
+                                             _ptr(self.state), _ptr(self.avg), _ptr(self.stats), _ptr(out), st),
+                   "epde_train_epilogue")
+
     def step(self, idx, lr, alpha):
         e = self.e
         B = len(idx)
+        alpha = float(alpha)
         if self._idx_dev is None or self._idx_dev.numel() != B:
             self._idx_dev = torch.empty(B, dtype=torch.int64, device=e.device)
-        self._idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)))
-        out, grad = e.step_device(self._idx_dev, B, self.p, float(alpha))
-        st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
-        # the reference averages the parameters AFTER the optimiser step of the same iteration (:277, :284)
-        self.t += 1
-        _lib.check(e.lib.epde_adam_step(_ptr(self.p), _ptr(grad), _ptr(self.m), _ptr(self.v), C.c_int64(e.n_params),
-                                        C.c_double(lr), C.c_int64(self.t), st), "epde_adam_step")
-        _lib.check(e.lib.epde_average_accumulate(C.byref(e.desc), _ptr(self.avg), _ptr(self.p), _ptr(out), st),
-                   "epde_average_accumulate")
-        _lib.check(e.lib.epde_eig_stats_accumulate(C.byref(e.desc), _ptr(self.stats), _ptr(out), st),
-                   "epde_eig_stats_accumulate")
+            self._pin = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(4)]
+            self._pin_ev = [None] * 4
+            self._graph = self._graph_key = self._seen_key = None
+        if lr != self._lr:
+            self.state[0:1].fill_(float(lr))
+            self._lr = lr
+        j = self._pin_i = (self._pin_i + 1) & 3
+        if self._pin_ev[j] is not None:
+            self._pin_ev[j].synchronize()                    # the upload that last used this pinned buffer is done
+        self._pin[j].numpy()[:] = idx
+        self._idx_dev.copy_(self._pin[j], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(e.device)); self._pin_ev[j] = ev
+        key = (B, alpha)
+        if not self.use_graph:
+            self._launch(B, alpha)
+        elif self._graph_key == key:
+            self._graph.replay()
+        elif self._seen_key == key:                          # second step of this (B, alpha): record, then replay
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(B, alpha)
+            self._graph, self._graph_key = g, key
+            g.replay()
+        else:                                                # first step: eager (allocates the workspace, sets attributes)
+            self._launch(B, alpha)
+            self._seen_key = key
         self.steps_in_stage += 1
+
+    @property
+    def t(self):
+        """Optimiser steps taken so far (synchronises)."""
+        return int(self.state[1].item())
 
     def read_scalars(self):
         """Host copy of the last step's (eig_vals, cvec, loss, non_penalty, penalty); synchronises."""

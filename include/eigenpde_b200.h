@@ -176,6 +176,12 @@ int epde_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float
  *                            cvec is read from d_out_scalars on the device), d_avg is fp64 [param_count]
  *   epde_eig_stats_accumulate: d_stats[0..k) += eig, d_stats[k..2k) += eig^2   (:280-282)
  */
+/*
+ * The three calls above in one launch with launch-invariant arguments (CUDA-graph replay of a whole training step):
+ * d_state[0] = learning rate, d_state[1] = number of optimiser steps taken so far (fp64, incremented by the call).
+ */
+int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_grad, float* d_m, float* d_v,
+                        double* d_state, double* d_avg, double* d_stats, const double* d_out_scalars, void* stream);
 int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d_params,
                             const double* d_out_scalars, void* stream);
 int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
