@@ -141,6 +141,32 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// ---- packed (f32x2) element-wise helpers over feature pairs: half the issue slots of the scalar forms ----------
+// tanh of two values + t = 1 - a^2 (FMUL2, 2 x EX2, FADD2, 2 x RCP, FFMA2, FFMA2)
+__device__ __forceinline__ void tanh_pair(float z0, float z1, float& a0, float& a1, float& t0, float& t1) {
+#ifdef EPDE_FAST_TANH
+  const float2 s = fmul2(make_float2(z0, z1), splat(2.885390081777927f));
+  float e0, e1, r0, r1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s.y));
+  const float2 ep = fadd2(make_float2(e0, e1), splat(1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(ep.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(ep.y));
+  const float2 a = ffma2(splat(-2.0f), make_float2(r0, r1), splat(1.0f));
+  const float2 t = ffma2(make_float2(-a.x, -a.y), a, splat(1.0f));
+  a0 = a.x; a1 = a.y; t0 = t.x; t1 = t.y;
+#else
+  a0 = tanhf(z0); a1 = tanhf(z1); t0 = fmaf(-a0, a0, 1.f); t1 = fmaf(-a1, a1, 1.f);
+#endif
+}
+// round-to-nearest TF32 split of two values (the integer part cannot be packed, the subtraction can)
+__device__ __forceinline__ void split_pair(float x0, float x1, float& h0, float& h1, float& l0, float& l1) {
+  h0 = __uint_as_float((__float_as_uint(x0) + 0x1000u) & 0xFFFFE000u);
+  h1 = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xFFFFE000u);
+  const float2 l = fadd2(make_float2(x0, x1), make_float2(-h0, -h1));
+  l0 = l.x; l1 = l.y;
+}
+
 // ---- packed weight image of one net (floats) -------------------------------------------------
 // Every matrix is the K-major, no-swizzle image of B[n][k] (n < 32 output columns of the MMA, k contraction):
 //   element (n, k) at (n / 8) * (K / 4) * 32 + (k / 4) * 32 + (n % 8) * 4 + (k % 4)      (floats)
@@ -236,7 +262,7 @@ __device__ __forceinline__ void issue_matvec_rt(int ksteps, uint32_t d_t, uint32
 __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, const float (&v)[TKH]) {
   float hi[TKH], lo[TKH];
 #pragma unroll
-  for (int i = 0; i < TKH; i++) split_tf32(v[i], hi[i], lo[i]);
+  for (int i = 0; i < TKH; i += 2) split_pair(v[i], v[i + 1], hi[i], hi[i + 1], lo[i], lo[i + 1]);
   tm_st24(ahi_t, hi); tm_st24(alo_t, lo);
   wait_st();
 }
@@ -342,36 +368,43 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     // ---- a1 ---------------------------------------------------------------------------------
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
-    for (int i = 0; i < H; i++) { v[i] = tanh1(z[i]); t1[i] = fmaf(-v[i], v[i], 1.f); }
+    for (int i = 0; i < H; i += 2) tanh_pair(z[i], z[i + 1], v[i], v[i + 1], t1[i], t1[i + 1]);
     v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(0))
     // ---- a2 ---------------------------------------------------------------------------------
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
-    for (int i = 0; i < H; i++) { v[i] = tanh1(z[i]); t2[i] = fmaf(-v[i], v[i], 1.f); }
+    for (int i = 0; i < H; i += 2) tanh_pair(z[i], z[i + 1], v[i], v[i + 1], t2[i], t2[i + 1]);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(1))
     // ---- a3, y, g3 --------------------------------------------------------------------------
     tm_ld20(tl + dcol, z); TC_ADD(5);
-    float y = b4r;
+    float y;
+    {
+      float2 yy = make_float2(b4r, 0.f);
 #pragma unroll
-    for (int i = 0; i < H; i++) {
-      const float a3 = tanh1(z[i]);
-      y = fmaf(w4r[i], a3, y);
-      v[i] = fmaf(-a3, a3, 1.f) * w4r[i];                             // g3 = (1 - a3^2) w4
+      for (int i = 0; i < H; i += 2) {
+        float a30, a31, t30, t31;
+        tanh_pair(z[i], z[i + 1], a30, a31, t30, t31);
+        const float2 w2 = make_float2(w4r[i], w4r[i + 1]);
+        yy = ffma2(w2, make_float2(a30, a31), yy);
+        const float2 g3 = fmul2(make_float2(t30, t31), w2);           // g3 = (1 - a3^2) w4
+        v[i] = g3.x; v[i + 1] = g3.y;
+      }
+      y = yy.x + yy.y;
     }
     v[20] = 0.f;
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(3))                                  // u2 = W3^T g3
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
-    for (int i = 0; i < H; i++) v[i] = t2[i] * z[i];                  // g2
+    for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t2[i], t2[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g2
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(2))                                  // u1 = W2^T g2
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
-    for (int i = 0; i < H; i++) v[i] = t1[i] * z[i];                  // g1
+    for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t1[i], t1[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g1
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(4))                                  // K g1
     tm_ld20(tl + dcol, z); TC_ADD(5);
