@@ -186,7 +186,15 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--knets", type=int, default=3, help="k (default 3 = the headline workload; 6 with --batch 2097152 on "
+                                                         "8 GPUs = BASELINE config 4, an ad-hoc run, not the bench line)")
     args = ap.parse_args()
+    if args.knets != 3:
+        global KNETS, EIG_W, FLOP_ALG, FLOP_ALG_P1
+        KNETS = args.knets
+        EIG_W = [1.0, 0.8, 0.6, 0.3, 0.2, 0.1][:KNETS]
+        FLOP_ALG = 2 * KNETS * (6 * M_MACS - 50 * 20)
+        FLOP_ALG_P1 = 2 * KNETS * 2 * M_MACS
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,7 +328,7 @@ def main():
         "metric": "samples/s, fused loss+grad step, 50-D k=3", "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ex1_50d_k3", "d": D, "k": KNETS, "arch": ARCH, "activation": "Tanh",
+        "config": {"workload": "ex1_50d_k%d" % KNETS, "d": D, "k": KNETS, "arch": ARCH, "activation": "Tanh",
                    "batch_per_gpu": B, "global_batch": world * B, "dataset_rows": K_DATA,
                    "parallelism": "dp%d (batch sharded, 2 NCCL allreduces/step)" % world if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: 872 MB data set gathered by fresh random indices each step"},
