@@ -109,6 +109,13 @@ cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt
 // gather + transpose the minibatch rows into the tile-major copy (workspace xt / wt)
 cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                           float* xt, float* wt, cudaStream_t st, int tile128 = 0) {
+  if (tile128) {     // tensor-core family: 128-sample tiles, wt padded to whole 256-sample tiles by the workspace layout
+    const size_t sm1 = (size_t)128 * (D->d_pad + 1) * 4;
+    cudaError_t e1 = cudaFuncSetAttribute(k_gather128<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    if (e1 != cudaSuccess) return e1;
+    k_gather128<0><<<(unsigned)((B + 127) / 128), 256, sm1, st>>>(X, w, idx, B, D->d_pad, xt, wt);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)GT * (D->d_pad + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

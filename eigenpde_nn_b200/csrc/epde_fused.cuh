@@ -139,6 +139,40 @@ k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t
   for (int j = 0; j < d_pad; j++) out[(size_t)j * GT + t] = ts[t * ld + j];
 }
 
+// k_gather128: the same for the tensor-core family: one CTA per 128-sample tile, 256 threads, 27 KB of shared memory
+// -> 8 CTAs = 64 warps per SM (k_gather: 4 CTAs = 32 warps), more row loads in flight for the DRAM-bound gather.
+// Output: xt[tile128][j][128] (one contiguous block per tile), wt[n].
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256)
+k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+            int d_pad, float* __restrict__ xt, float* __restrict__ wt) {
+  extern __shared__ float4 smem4[];
+  float* ts = reinterpret_cast<float*>(smem4);           // [128][d_pad + 1]
+  __shared__ int64_t srow[128];
+  const int ld = d_pad + 1, nq = d_pad >> 2, t = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  if (t < 128) {
+    const int64_t n = tile * 128 + t;
+    const bool v = n < B;
+    const int64_t r = v ? (idx ? idx[n] : n) : 0;
+    srow[t] = v ? r : -1;
+    wt[n] = v ? (w ? w[r] : 1.f) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int c = t; c < 128 * nq; c += 256) {
+    const int row = c / nq, q = c - row * nq;
+    const int64_t rr = srow[row];
+    const float4 val = (rr >= 0) ? __ldg(reinterpret_cast<const float4*>(X + rr * d_pad) + q)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dst = ts + row * ld + 4 * q;
+    dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
+  }
+  __syncthreads();
+  float* out = xt + (size_t)tile * d_pad * 128 + (t & 127);
+  for (int j = (t >> 7); j < d_pad; j += 2) out[(size_t)j * 128] = ts[(t & 127) * ld + j];
+}
+
 // layer 1: a1 = tanh(W1 x + b1); x_j of the sample pair is one coalesced float2 of the transposed
 // tile, software-pipelined PF columns ahead of the FFMA2 stream.
 template <int H, int PF = 8>
