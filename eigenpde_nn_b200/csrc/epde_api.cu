@@ -162,8 +162,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
     rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx,
                     (D->flags & EPDE_FLAG_DETERMINISTIC) ? 1 : 0, st);
     if (rc) return rc;
-    const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
-    k_fin2<kFusedH><<<D->k, 512, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+    const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
+    k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
     return (int)cudaGetLastError();
   }
   const int64_t ntiles = (B + P2_T - 1) / P2_T;
@@ -175,8 +175,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
                                                               W.coef, W.pg);
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
-  const size_t sm2 = (size_t)GradLayout<kFusedH>(D->d_pad).total() * 8;
-  k_fin2<kFusedH><<<D->k, 512, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+  const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
+  k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
   return (int)cudaGetLastError();
 }
 

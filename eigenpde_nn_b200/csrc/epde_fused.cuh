@@ -713,35 +713,38 @@ template <int H>
 __global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
                        const float* __restrict__ params, const float* __restrict__ diag_coeff,
                        float* __restrict__ grad) {
-  extern __shared__ double sred[];
+  // grid = (K, S): CTA (net, s) produces the flat-gradient elements e = s, s + S, ... of its net.  Every CTA reduces
+  // Gamma (H x H) itself - the dW1 correction needs all of it - and only its own share of the other accumulators.
+  extern __shared__ double sred[];               // [H * H] Gamma
   const GradLayout<H> G(d_pad);
   const int gn = G.total();
-  const int net = blockIdx.x;
-  for (int e = threadIdx.x; e < gn; e += blockDim.x) {
+  const int net = blockIdx.x, S = gridDim.y, sl = blockIdx.y;
+  auto red = [&](int e) {
     double s = 0.0;
     for (int c = 0; c < ncta; c++) s += (double)pg[((size_t)c * K + net) * gn + e];
-    sred[e] = s;
-  }
+    return s;
+  };
+  for (int e = threadIdx.x; e < H * H; e += blockDim.x) sred[e] = red(G.Gam() + e);
   __syncthreads();
   const int fn = flat_net_size<H>(d);
   const float* W1 = params + (size_t)net * fn;
   float* g = grad + (size_t)net * fn;
-  for (int e = threadIdx.x; e < fn; e += blockDim.x) {
+  for (int e = sl * blockDim.x + threadIdx.x; e < fn; e += S * blockDim.x) {
     double v;
     if (e < H * d) {
       const int o = e / d, j = e % d;
       double corr = 0.0;
-      for (int b = 0; b < H; b++) corr += sred[G.Gam() + o * H + b] * (double)W1[b * d + j];
-      v = sred[G.gW1() + o * d_pad + j] + 2.0 * (double)diag_coeff[j] * corr;
+      for (int b = 0; b < H; b++) corr += sred[o * H + b] * (double)W1[b * d + j];
+      v = red(G.gW1() + o * d_pad + j) + 2.0 * (double)diag_coeff[j] * corr;
     } else {
       int r = e - H * d;
-      if (r < H) v = sred[G.gb1() + r];
-      else if ((r -= H) < H * H) v = sred[G.gW2() + r];
-      else if ((r -= H * H) < H) v = sred[G.gb2() + r];
-      else if ((r -= H) < H * H) v = sred[G.gW3() + r];
-      else if ((r -= H * H) < H) v = sred[G.gb3() + r];
-      else if ((r -= H) < H) v = sred[G.gw4() + r];
-      else v = sred[G.gb4()];
+      if (r < H) v = red(G.gb1() + r);
+      else if ((r -= H) < H * H) v = red(G.gW2() + r);
+      else if ((r -= H * H) < H) v = red(G.gb2() + r);
+      else if ((r -= H) < H * H) v = red(G.gW3() + r);
+      else if ((r -= H * H) < H) v = red(G.gb3() + r);
+      else if ((r -= H) < H) v = red(G.gw4() + r);
+      else v = red(G.gb4());
     }
     g[e] = (float)v;
   }

@@ -37,7 +37,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
     case 5: k_sums_y<5><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
     default: k_sums_y<6><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
   }
-  k_reduce_tc<<<1, 64, 0, st>>>(part, gx, part2, g2, k, sums);
+  k_reduce_tc<<<1, 1024, 0, st>>>(part, gx, part2, g2, k, sums);      // one warp per sum (34 sums for k = 6)
   return (int)cudaGetLastError();
 }
 

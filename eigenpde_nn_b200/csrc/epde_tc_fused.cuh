@@ -468,20 +468,25 @@ k_sums_y(const float* __restrict__ wt, const float* __restrict__ ybuf, int64_t B
   }
 }
 
-// sums = [W, S1(k), E(k), S2(k(k+1)/2)] from the two partial arrays, fixed order
-__global__ void k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K,
-                            double* __restrict__ sums) {
-  const int s = threadIdx.x, ns2 = 1 + K * (K + 1) / 2, ns = 1 + 2 * K + K * (K + 1) / 2;
-  if (s >= ns) return;
-  double v = 0.0;
-  if (s == 0 || s > 2 * K) {
-    const int c = (s == 0) ? 0 : s - 2 * K;
-    for (int b = 0; b < g2; b++) v += part2[(size_t)b * ns2 + c];
-  } else {
-    const int net = (s - 1) % K, which = (s - 1) / K;
-    for (int b = 0; b < gx; b++) v += part[((size_t)net * gx + b) * 2 + which];
+// sums = [W, S1(k), E(k), S2(k(k+1)/2)] from the two partial arrays; one warp per sum, fixed (lane-strided, then
+// shuffle-tree) order
+__global__ void __launch_bounds__(1024)
+k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K,
+            double* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int ns2 = 1 + K * (K + 1) / 2, ns = 1 + 2 * K + K * (K + 1) / 2;       // 34 sums for k = 6
+  for (int s = threadIdx.x >> 5; s < ns; s += blockDim.x >> 5) {
+    double v = 0.0;
+    if (s == 0 || s > 2 * K) {
+      const int c = (s == 0) ? 0 : s - 2 * K;
+      for (int b = lane; b < g2; b += 32) v += part2[(size_t)b * ns2 + c];
+    } else {
+      const int net = (s - 1) % K, which = (s - 1) / K;
+      for (int b = lane; b < gx; b += 32) v += part[((size_t)net * gx + b) * 2 + which];
+    }
+    v = warp_sum(v);
+    if (lane == 0) sums[s] = v;
   }
-  sums[s] = v;
 }
 
 }  // namespace tc
