@@ -720,8 +720,16 @@ __global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int
   const int gn = G.total();
   const int net = blockIdx.x, S = gridDim.y, sl = blockIdx.y;
   auto red = [&](int e) {
-    double s = 0.0;
-    for (int c = 0; c < ncta; c++) s += (double)pg[((size_t)c * K + net) * gn + e];
+    double s = 0.0;                              // fixed order; the loads of eight CTAs are in flight together
+    int c = 0;
+    for (; c + 8 <= ncta; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
+#pragma unroll
+      for (int q = 0; q < 8; q++) s += (double)v[q];
+    }
+    for (; c < ncta; c++) s += (double)__ldg(pg + ((size_t)c * K + net) * gn + e);
     return s;
   };
   for (int e = threadIdx.x; e < H * H; e += blockDim.x) sred[e] = red(G.Gam() + e);
