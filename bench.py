@@ -130,6 +130,14 @@ def cpu_port_rate(B, steps, warmup, seed=0):
     import numpy as np
     import torch
     from oracle import ref_port
+    # all host threads the box offers: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make the CPU arm
+    # single-threaded in the N > 1 runs
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     rng = np.random.default_rng(seed)
     Kd = max(4 * B, 100000)
     X = np.sqrt(0.1) * rng.standard_normal((Kd, D))
