@@ -21,7 +21,7 @@ FLAG_DETERMINISTIC = 2
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
            "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
-           "epde_eig_stats_accumulate", "epde_set_fused_impl", "epde_md_align", "epde_train_epilogue"]
+           "epde_eig_stats_accumulate", "epde_set_fused_impl", "epde_md_align", "epde_train_epilogue", "epde_peer_allreduce"]
 
 
 class EpdeDesc(C.Structure):
@@ -62,6 +62,7 @@ def lib():
         L.epde_average_accumulate.argtypes = [dp, vp, vp, vp, vp]
         L.epde_eig_stats_accumulate.argtypes = [dp, vp, vp, vp]
         L.epde_set_fused_impl.argtypes = [C.c_int]
+        L.epde_peer_allreduce.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, vp, vp, i64, C.c_int, i64, vp]
         L.epde_train_epilogue.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.epde_md_align.argtypes = [i64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp]
         for name in EXPORTS:

@@ -191,6 +191,42 @@ int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, 
   return EPDE_OK;
 }
 
+// ---- one-shot all-reduce over NVLink peer memory (the two tiny exchanges of the sharded step) --------------------------
+// Every rank owns one symmetric buffer [256 B of flags | 2 parities x world slots x slot_bytes].  A call (epoch e, parity
+// e & 1) stores this rank's payload into slot[rank] of EVERY rank's buffer with plain peer stores, fences, raises
+// flag[parity][rank] = e in every rank's buffer, waits until all world flags of its OWN buffer show e, and sums the world
+// slots in rank order (the same order on every rank: bit-identical results everywhere).  A rank cannot run two epochs
+// ahead of a peer (it needs that peer's flag for e+1, raised only after the peer finished e), so two parities suffice.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t epoch, const T* __restrict__ src,
+                 T* __restrict__ dst, int n, int64_t slot_bytes) {
+  const int par = epoch & 1;
+  const int64_t data_off = 256 + ((int64_t)par * world + rank) * slot_bytes;
+  for (int p = 0; p < world; p++) {
+    T* slot = reinterpret_cast<T*>(bufs[p] + data_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    volatile uint32_t* theirs = reinterpret_cast<volatile uint32_t*>(bufs[threadIdx.x]) + par * world + rank;
+    *theirs = epoch;
+    __threadfence_system();
+    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(bufs[rank]) + par * world + threadIdx.x;
+    int spin = 0;
+    while (*mine != epoch) { __nanosleep(64); if (++spin > (1 << 24)) __trap(); }    // bounded (~1 s): a lost peer traps
+  }
+  __syncthreads();
+  __threadfence_system();
+  const char* base = bufs[rank] + 256 + (int64_t)par * world * slot_bytes;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    T v = 0;
+    for (int p = 0; p < world; p++) v += reinterpret_cast<const volatile T*>(base + (int64_t)p * slot_bytes)[i];
+    dst[i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -420,6 +456,17 @@ __global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p,
 __global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict__ out, int k) {
   const int i = threadIdx.x;
   if (i < k) { const double e = out[EPDE_OUT_EIG(k) + i]; stats[i] += e; stats[k + i] += e * e; }
+}
+
+int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
+                        int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
+  if (!d_peer_bufs || !src || !dst) return EPDE_ERR_NULL;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || n < 1 || epoch == 0 ||
+      n * (is_f64 ? 8 : 4) > slot_bytes || (slot_bytes & 15)) return EPDE_ERR_ARG;
+  char* const* bufs = reinterpret_cast<char* const*>(d_peer_bufs);
+  if (is_f64) k_peer_allreduce<double><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, (const double*)src, (double*)dst, (int)n, slot_bytes);
+  else k_peer_allreduce<float><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, (const float*)src, (float*)dst, (int)n, slot_bytes);
+  return (int)cudaGetLastError();
 }
 
 int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* X, const double* ref_x, const int32_t* ref_index,

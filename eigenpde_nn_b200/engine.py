@@ -79,6 +79,10 @@ class StepEngine:
             self.grad = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
         self._ws = None
         self._ws_B = 0
+        self._exchange = None
+        if self.pg is not None:
+            from .parallel import PeerExchange
+            self._exchange = PeerExchange.create(self.lib, self.pg, self.device)
         self._eigw_c = (C.c_double * self.k)(*self.eig_w)
 
     # -- buffers ------------------------------------------------------------------------------
@@ -124,7 +128,7 @@ class StepEngine:
                                                      _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()),
                                                      _ptr(self.out), _ptr(self.grad), st), "epde_step_finish")
 
-            two_phase_step(partial, finish, self.sums, self.grad, self.pg)
+            two_phase_step(partial, finish, self.sums, self.grad, self.pg, self._exchange)
         return self.out, self.grad
 
     def step(self, idx, params_dev, alpha):

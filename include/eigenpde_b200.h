@@ -187,6 +187,17 @@ int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d
 int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
 
 /*
+ * One-shot all-reduce (sum) of a small vector over NVLink peer memory, for the two exchanges of the sharded step
+ * (the 1 + 2k + k(k+1)/2 fp64 partial sums between the phases, the fp32 gradient after phase 2).
+ * d_peer_bufs: DEVICE array of `world` pointers, entry p = rank p's symmetric buffer mapped into this process
+ * (e.g. torch.distributed._symmetric_memory: rendezvous(...).buffer_ptrs_dev); every buffer is
+ * 256 + 2 * world * slot_bytes bytes and zero-filled before the first call.  epoch = 1, 2, 3, ... must advance by one
+ * per call on every rank.  In place (src == dst) is allowed.  A peer that never arrives traps after about a second.
+ */
+int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
+                        int64_t n, int is_f64, int64_t slot_bytes, void* stream);
+
+/*
  * MD pre-processing layer `MD_data_set.align` (src/data_set.py:126-153; called from every net's forward,
  * src/network_arch.py:62): Kabsch alignment of each configuration (n_atoms x 3 coordinates per row of d_X) to the
  * reference configuration ref_x[m][3] over the atoms ref_index[m] (file format: load_ref_state :112-124).
