@@ -215,7 +215,7 @@ k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t e
     __threadfence_system();
     volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(bufs[rank]) + par * world + threadIdx.x;
     int spin = 0;
-    while (*mine != epoch) { __nanosleep(64); if (++spin > (1 << 24)) __trap(); }    // bounded (~1 s): a lost peer traps
+    while (*mine != epoch) { __nanosleep(128); if (++spin > (1 << 28)) __trap(); }   // bounded (~1 min): a lost peer traps
   }
   __syncthreads();
   __threadfence_system();
