@@ -137,3 +137,25 @@ def test_fused_family_switch(L):
     assert L.epde_set_fused_impl(1) == 0
     assert L.epde_set_fused_impl(2) == -6
     assert L.epde_set_fused_impl(-1) == -6
+
+
+def test_argument_validation_of_the_newer_entry_points(L):
+    """NULL / range checks happen before any launch, so they can be exercised without a GPU."""
+    from eigenpde_nn_b200 import _lib
+    null = C.c_void_p(0)
+    one = C.c_void_p(8)                      # any non-NULL address: the calls below must fail before touching it
+    # epde_peer_allreduce: NULL pointers, epoch 0, rank out of range, payload larger than a slot, slot misaligned
+    assert L.epde_peer_allreduce(null, 0, 2, 1, one, one, 13, 1, 65536, null) == -1
+    assert L.epde_peer_allreduce(one, 0, 2, 0, one, one, 13, 1, 65536, null) == -6
+    assert L.epde_peer_allreduce(one, 2, 2, 1, one, one, 13, 1, 65536, null) == -6
+    assert L.epde_peer_allreduce(one, 0, 2, 1, one, one, 9000, 1, 65536, null) == -6
+    assert L.epde_peer_allreduce(one, 0, 2, 1, one, one, 13, 1, 65530, null) == -6
+    # epde_md_align: NULL pointers, too many atoms, reference index out of range
+    ref = (C.c_double * 9)(*([0.0] * 9)); ri = (C.c_int32 * 3)(0, 1, 2); bad = (C.c_int32 * 3)(0, 1, 11)
+    assert L.epde_md_align(10, 10, 32, null, ref, ri, 3, one, one, null, null) == -1
+    assert L.epde_md_align(10, 40, 120, one, ref, ri, 3, one, one, null, null) == -6
+    assert L.epde_md_align(10, 10, 32, one, ref, bad, 3, one, one, null, null) == -6
+    assert L.epde_md_align(10, 10, 28, one, ref, ri, 3, one, one, null, null) == -6          # d_pad < 3 * n_atoms
+    # epde_train_epilogue: descriptor and pointer checks
+    desc = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
+    assert L.epde_train_epilogue(C.byref(desc), null, one, one, one, one, one, one, one, null) == -1

@@ -455,3 +455,51 @@ def test_md_align_kernel_and_metric_step_vs_reference():
     res = eng.step(g["idx"], _flat(g["params"]), g["alpha"])
     grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), g["arch"], g["k"])
     check_step_against(g, res, TOL, grads)
+
+
+def test_train_epilogue_equals_separate_calls():
+    """epde_train_epilogue (one launch, device-side learning rate / step count) against epde_adam_step +
+    epde_average_accumulate + epde_eig_stats_accumulate."""
+    import ctypes as C
+    from eigenpde_nn_b200 import _lib
+    L = _lib.lib()
+    k, arch = 3, [50, 20, 20, 20, 1]
+    desc = _lib.make_desc(arch, k, "Tanh", 52)
+    n = C.c_int64(); _lib.check(L.epde_param_count(C.byref(desc), C.byref(n)), "count"); n = n.value
+    g = torch.Generator().manual_seed(5)
+    p1 = torch.randn(n, generator=g).cuda(); p2 = p1.clone()
+    m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda"); m2 = m1.clone(); v2 = v1.clone()
+    avg1 = torch.zeros(n, dtype=torch.float64, device="cuda"); avg2 = avg1.clone()
+    st1 = torch.zeros(2 * k, dtype=torch.float64, device="cuda"); st2 = st1.clone()
+    state = torch.tensor([5e-3, 0.0], dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 5):
+        grad = torch.randn(n, generator=g).cuda()
+        out = torch.zeros(4 + 4 * k, dtype=torch.float64)
+        out[4:4 + k] = torch.rand(k, generator=g, dtype=torch.float64)
+        out[4 + k:4 + 2 * k] = torch.randperm(k, generator=g).double()
+        out = out.cuda()
+        _lib.check(L.epde_adam_step(p1.data_ptr(), grad.data_ptr(), m1.data_ptr(), v1.data_ptr(), n, 5e-3, step, s), "adam")
+        _lib.check(L.epde_average_accumulate(C.byref(desc), avg1.data_ptr(), p1.data_ptr(), out.data_ptr(), s), "avg")
+        _lib.check(L.epde_eig_stats_accumulate(C.byref(desc), st1.data_ptr(), out.data_ptr(), s), "stats")
+        _lib.check(L.epde_train_epilogue(C.byref(desc), p2.data_ptr(), grad.data_ptr(), m2.data_ptr(), v2.data_ptr(),
+                                         state.data_ptr(), avg2.data_ptr(), st2.data_ptr(), out.data_ptr(), s), "epilogue")
+    assert float(state[1]) == 4.0
+    assert torch.allclose(p1, p2, rtol=1e-6, atol=1e-7) and torch.allclose(m1, m2) and torch.allclose(v1, v2)
+    assert torch.allclose(avg1, avg2, rtol=1e-6, atol=1e-7) and torch.equal(st1, st2)
+
+
+def test_minibatch_pipeline_delivers_every_batch():
+    from eigenpde_nn_b200.engine import MinibatchPipeline
+    B = 4096
+    pins = [torch.randint(0, 1 << 20, (B,), dtype=torch.int64).pin_memory() for _ in range(6)]
+    pipe = MinibatchPipeline(B, "cuda:0")
+    pipe.prefetch(pins[0])
+    for i in range(6):
+        got = pipe.acquire()
+        chk = got.clone()                       # consume on the current stream
+        pipe.release()
+        if i + 1 < 6:
+            pipe.prefetch(pins[i + 1])
+        torch.cuda.synchronize()
+        assert torch.equal(chk.cpu(), pins[i])

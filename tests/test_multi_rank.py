@@ -82,3 +82,20 @@ def test_two_rank_protocol_matches_single_rank(name):
     assert np.allclose(eig, g["eig_vals"], rtol=1e-10) and list(cvec) == list(g["cvec"])
     ref = closed_form.flatten(g["grads"])
     assert np.linalg.norm(grad - ref) / np.linalg.norm(ref) < 1e-9
+
+
+def test_peer_exchange_declines_without_nccl():
+    """PeerExchange.create returns None (-> the two collective calls) when symmetric memory cannot be used: a gloo
+    group on CPU here; `two_phase_step` then takes the dist.all_reduce path exercised above."""
+    import torch.distributed as dist
+    from eigenpde_nn_b200.parallel import PeerExchange
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29611", rank=0, world_size=1)
+        made = True
+    else:
+        made = False
+    try:
+        assert PeerExchange.create(None, dist.group.WORLD, "cpu") is None
+    finally:
+        if made:
+            dist.destroy_process_group()
