@@ -7,6 +7,7 @@
 // (g_gemm).  Weight gradients accumulate in fp64 (atomicAdd on doubles) across chunks.
 // Same two-phase structure and the same batch sums as the fused path.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,6 +16,9 @@
 #include "epde_tc_gemm.cuh"
 
 namespace epde {
+
+// CTAs a split-K weight-gradient GEMM is cut into (dev knob EPDE_TC_SPLIT; 3 CTAs of g_gemm_tc fit on one SM)
+static int g_tc_split_target = -1;
 
 // ---- activations: value, first and second derivative as functions of z ----------------------
 // torch.nn defaults (ELU/CELU alpha = 1, Softplus beta = 1 threshold = 20)
@@ -288,7 +292,7 @@ inline GenericPlan generic_plan(const epde_desc* D, int64_t B, void* base) {
   P.Gb = (float*)take((size_t)bc * P.maxn * 4);
   P.T = (float*)take((size_t)bc * P.maxn * 4);
   P.ones = (float*)take((size_t)bc * 4);
-  P.cpart_floats = (size_t)64 * P.maxn * P.maxn;
+  P.cpart_floats = (size_t)128 * P.maxn * P.maxn;
   if (P.cpart_floats > ((size_t)16 << 20)) P.cpart_floats = (size_t)16 << 20;
   P.cpart = (float*)take(P.cpart_floats * 4);
   for (int l = 1; l <= P.L; l++) {
@@ -329,10 +333,11 @@ inline void gemm(cudaStream_t st, const TcCtx& tc, int M, int N, int K, const fl
       g_gemm_tc<TA, TB><<<dim3(nt, mt, 1), TC_THREADS, TC_SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, K, 0);
     } else {
       // split K over enough CTAs to fill the chip; partial tiles in fp32, summed into fp64 afterwards
-      int nz = (160 + mt * nt - 1) / (mt * nt);
+      if (g_tc_split_target < 0) { const char* e_ = getenv("EPDE_TC_SPLIT"); g_tc_split_target = (e_ && atoi(e_) > 0) ? atoi(e_) : 296; }
+      int nz = (g_tc_split_target + mt * nt - 1) / (mt * nt);
       const int maxz = (K + 255) / 256;
       if (nz > maxz) nz = maxz;
-      if (nz > 64) nz = 64;
+      if (nz > 128) nz = 128;
       while (nz > 1 && (size_t)nz * M * N > tc.cap) nz--;
       int ksplit = ((K + nz - 1) / nz + TC_BK - 1) / TC_BK * TC_BK;
       nz = (K + ksplit - 1) / ksplit;

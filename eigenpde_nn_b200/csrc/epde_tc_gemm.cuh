@@ -75,7 +75,7 @@ __device__ __forceinline__ void tc_tile_load(const float* __restrict__ src, int 
       const int gm = mn0 + e / (int)TC_KCH, gk = k0 + 4 * (e % (int)TC_KCH);
       if (gm < mn_end && gk < k_end) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gm * ld + gk));
     } else {
-      const int gk = k0 + (e >> 5), gm = mn0 + 4 * (e & 31);
+      const int gk = k0 + 4 * (e >> 7) + (e & 3), gm = mn0 + 4 * ((e & 127) >> 2);     // see tc_tile_store
       if (gk < k_end && gm < mn_end) v[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)gk * ld + gm));
     }
   }
@@ -95,7 +95,9 @@ __device__ __forceinline__ void tc_tile_store(const float4 (&v)[TC_V], unsigned 
       *reinterpret_cast<float4*>(hi + off) = h;
       *reinterpret_cast<float4*>(lo + off) = l;
     } else {
-      const int k = e >> 5, mc = e & 31;
+      // a warp covers 4 k x 8 float4 of mn (four 128-byte row segments in global memory): its 32 scalar stores of
+      // one j then hit 32 different banks (k & 3 -> word, (mc & 1) -> +16 words, mc / 2 -> +4 words per 8-row group)
+      const int k = 4 * (e >> 7) + (e & 3), mc = (e & 127) >> 2;
       const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
       for (int j = 0; j < 4; j++) {
