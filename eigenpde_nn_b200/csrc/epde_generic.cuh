@@ -108,10 +108,19 @@ __global__ void g_gather(const float* __restrict__ X, const int64_t* __restrict_
   const int64_t r = idx ? idx[b0 + b] : b0 + b;
   Xc[e] = X[r * d_pad + j];
 }
+// The element-wise kernels below handle four consecutive elements per thread (one 16-byte access per array when the
+// whole group is in range; every workspace array is 256-byte aligned), launched with g_blocks4(n).
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __global__ void g_act(int act, int64_t n, const float* __restrict__ Z, float* __restrict__ Aout) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e >= n) return;
-  float v, d1, d2; act_eval(act, Z[e], v, d1, d2); Aout[e] = v;
+  float v, d1, d2;
+  if (e + 3 < n) {
+    const float4 z = ld4(Z + e); float4 a;
+    act_eval(act, z.x, a.x, d1, d2); act_eval(act, z.y, a.y, d1, d2); act_eval(act, z.z, a.z, d1, d2); act_eval(act, z.w, a.w, d1, d2);
+    st4(Aout + e, a);
+  } else for (int64_t i = e; i < n; i++) { act_eval(act, Z[i], v, d1, d2); Aout[i] = v; }
 }
 __global__ void g_fill(int64_t n, float v, float* __restrict__ o) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,9 +129,15 @@ __global__ void g_fill(int64_t n, float v, float* __restrict__ o) {
 // G = phi'(Z) * U
 __global__ void g_jacmul(int act, int64_t n, const float* __restrict__ Z, const float* __restrict__ U,
                          float* __restrict__ Gout) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e >= n) return;
-  float v, d1, d2; act_eval(act, Z[e], v, d1, d2); Gout[e] = d1 * U[e];
+  float v, d1, d2;
+  if (e + 3 < n) {
+    const float4 z = ld4(Z + e), u = ld4(U + e); float4 g;
+    act_eval(act, z.x, v, d1, d2); g.x = d1 * u.x; act_eval(act, z.y, v, d1, d2); g.y = d1 * u.y;
+    act_eval(act, z.z, v, d1, d2); g.z = d1 * u.z; act_eval(act, z.w, v, d1, d2); g.w = d1 * u.w;
+    st4(Gout + e, g);
+  } else for (int64_t i = e; i < n; i++) { act_eval(act, Z[i], v, d1, d2); Gout[i] = d1 * U[i]; }
 }
 // Wp[r][c] = c < cols ? W[r][c] : 0   (row length padded to ldp)
 __global__ void g_pad_weights(int rows, int cols, int ldp, const float* __restrict__ W, float* __restrict__ Wp) {
@@ -207,19 +222,34 @@ __global__ void g_seed(int Bc, int d, int ldu, const float* __restrict__ U0, con
 // Ubar_l = phi'(Z_l) Gbar_l ; Zbar_l = phi''(Z_l) U_l Gbar_l
 __global__ void g_esweep(int act, int64_t n, const float* __restrict__ Z, const float* __restrict__ U,
                          const float* __restrict__ Gbar, float* __restrict__ Ubar, float* __restrict__ Zbar) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e >= n) return;
-  float v, d1, d2; act_eval(act, Z[e], v, d1, d2);
-  const float gb = Gbar[e];
-  Ubar[e] = d1 * gb; Zbar[e] = d2 * U[e] * gb;
+  float v, d1, d2;
+  if (e + 3 < n) {
+    const float4 z = ld4(Z + e), u = ld4(U + e), gb = ld4(Gbar + e); float4 ub, zb;
+    act_eval(act, z.x, v, d1, d2); ub.x = d1 * gb.x; zb.x = d2 * u.x * gb.x;
+    act_eval(act, z.y, v, d1, d2); ub.y = d1 * gb.y; zb.y = d2 * u.y * gb.y;
+    act_eval(act, z.z, v, d1, d2); ub.z = d1 * gb.z; zb.z = d2 * u.z * gb.z;
+    act_eval(act, z.w, v, d1, d2); ub.w = d1 * gb.w; zb.w = d2 * u.w * gb.w;
+    st4(Ubar + e, ub); st4(Zbar + e, zb);
+  } else for (int64_t i = e; i < n; i++) {
+    act_eval(act, Z[i], v, d1, d2);
+    const float gb = Gbar[i];
+    Ubar[i] = d1 * gb; Zbar[i] = d2 * U[i] * gb;
+  }
 }
 // Zbar_{l-1} += phi'(Z_{l-1}) T
 __global__ void g_zsweep(int act, int64_t n, const float* __restrict__ Z, const float* __restrict__ T,
                          float* __restrict__ Zbar) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e >= n) return;
-  float v, d1, d2; act_eval(act, Z[e], v, d1, d2);
-  Zbar[e] += d1 * T[e];
+  float v, d1, d2;
+  if (e + 3 < n) {
+    const float4 z = ld4(Z + e), t = ld4(T + e); float4 zb = ld4(Zbar + e);
+    act_eval(act, z.x, v, d1, d2); zb.x += d1 * t.x; act_eval(act, z.y, v, d1, d2); zb.y += d1 * t.y;
+    act_eval(act, z.z, v, d1, d2); zb.z += d1 * t.z; act_eval(act, z.w, v, d1, d2); zb.w += d1 * t.w;
+    st4(Zbar + e, zb);
+  } else for (int64_t i = e; i < n; i++) { act_eval(act, Z[i], v, d1, d2); Zbar[i] += d1 * T[i]; }
 }
 // Zbar_L[b] = ybar_b = w_b (sum_j Cw[net][j] y_{b,j} - cm[net])
 __global__ void g_ybar(int Bc, int k, int net, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t b0,
@@ -312,6 +342,7 @@ inline int generic_workspace_bytes(const epde_desc* D, int64_t B, size_t* out) {
 }
 
 inline unsigned g_blocks(int64_t n) { return (unsigned)((n + 255) / 256); }
+inline unsigned g_blocks4(int64_t n) { return (unsigned)(((n + 3) / 4 + 255) / 256); }
 
 struct TcCtx { float* cpart; size_t cap; };
 
@@ -389,7 +420,7 @@ inline void generic_fwd_jac(const epde_desc* D, const GenericPlan& P, const NetP
     gemm<false, true>(st, tc, Bc, P.n[l], P.w[l - 1], Ain, P.w[l - 1], np.Wp[l], P.w[l - 1], P.Z[l], P.n[l], np.b[l],
                       nullptr);
     if (l < L) {
-      g_act<<<g_blocks((int64_t)Bc * P.n[l]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l], P.Z[l], P.A[l]);
+      g_act<<<g_blocks4((int64_t)Bc * P.n[l]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l], P.Z[l], P.A[l]);
       Ain = P.A[l];
     }
   }
@@ -400,7 +431,7 @@ inline void generic_fwd_jac(const epde_desc* D, const GenericPlan& P, const NetP
     gemm<false, false>(st, tc, Bc, P.w[l - 1], P.n[l], P.G[l], P.n[l], np.Wp[l], P.w[l - 1], Uout, P.w[l - 1], nullptr,
                        nullptr);
     if (l > 1)
-      g_jacmul<<<g_blocks((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l - 1], P.Z[l - 1],
+      g_jacmul<<<g_blocks4((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(D->act_id, (int64_t)Bc * P.n[l - 1], P.Z[l - 1],
                                                                    P.U[l - 1], P.G[l - 1]);
   }
 }
@@ -452,7 +483,7 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
           // gbar_l = W_l ubar_{l-1}
           gemm<false, true>(st, tc, Bc, P.n[l], P.w[l - 1], P.Ub, P.w[l - 1], np.Wp[l], P.w[l - 1], P.Gb, P.n[l], nullptr,
                             nullptr);
-          g_esweep<<<g_blocks((int64_t)Bc * P.n[l]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l], P.Z[l], P.U[l], P.Gb,
+          g_esweep<<<g_blocks4((int64_t)Bc * P.n[l]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l], P.Z[l], P.U[l], P.Gb,
                                                                    P.Ub, P.Zb[l]);
         }
       }
@@ -467,7 +498,7 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
         if (l > 1) {
           gemm<false, false>(st, tc, Bc, P.n[l - 1], P.n[l], P.Zb[l], P.n[l], np.Wp[l], P.w[l - 1], P.T, P.n[l - 1], nullptr,
                              nullptr);
-          g_zsweep<<<g_blocks((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l - 1], P.Z[l - 1], P.T,
+          g_zsweep<<<g_blocks4((int64_t)Bc * P.n[l - 1]), 256, 0, st>>>(act, (int64_t)Bc * P.n[l - 1], P.Z[l - 1], P.T,
                                                                        P.Zb[l - 1]);
         }
       }
