@@ -269,6 +269,38 @@ __global__ void g_colsum(int rows, int n, const float* __restrict__ Zb, double* 
   for (int r = r0; r < r1; r++) s += (double)Zb[(size_t)r * n + c];
   atomicAdd(&dacc[c], s);
 }
+// ---- products with a dimension of 1 (the output layer n_L = 1): streaming kernels instead of GEMM tiles -----------
+// C[m] = sum_k A[m][k] B[k] (+ bias[0]): one warp per row
+__global__ void __launch_bounds__(256)
+g_rowdot(int M, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, float* __restrict__ C, int ldc,
+         const float* __restrict__ bias) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float* a = A + (size_t)m * lda;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(a[k], B[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) C[(size_t)m * ldc] = s + (bias ? bias[0] : 0.f);
+}
+// C[m][n] = a[m] * b[n]   (K = 1)
+__global__ void g_outer1(int64_t M, int N, const float* __restrict__ a, int lda, const float* __restrict__ b,
+                         float* __restrict__ C, int ldc) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * N) return;
+  const int64_t m = e / N; const int n = (int)(e - m * N);
+  C[m * ldc + n] = a[m * lda] * b[n];
+}
+// dacc[n] += sum_k a[k] * B[k][n]   (M = 1, fp64): coalesced weighted column sums, one atomic per block and column
+__global__ void g_wcolsum(int rows, int n, int n_valid, const float* __restrict__ a, int lda, const float* __restrict__ Bm,
+                          int ldb, double* __restrict__ dacc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_valid) return;
+  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  double s = 0.0;
+  for (int r = r0; r < r1; r++) s += (double)(a[(size_t)r * lda] * Bm[(size_t)r * ldb + c]);
+  atomicAdd(&dacc[c], s);
+}
 __global__ void g_zero_d(int64_t n, double* __restrict__ o) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) o[e] = 0.0;
@@ -354,6 +386,16 @@ inline void gemm(cudaStream_t st, const TcCtx& tc, int M, int N, int K, const fl
   // n_valid (dacc mode): only the first n_valid of the N output columns are accumulated (N is the
   // zero-padded width of the operands); the accumulator has leading dimension ldc.
   if (n_valid < 0) n_valid = N;
+  // the output layer (n_L = 1) turns three kinds of products into streaming operations
+  if (!dacc && N == 1 && !TA && K >= 32) {                       // A [M x K] times a vector (B is [1][K] or [K][1])
+    if (TB || ldb == 1) { g_rowdot<<<(M + 7) / 8, 256, 0, st>>>(M, K, A, lda, B, C, ldc, bias); return; }
+  }
+  if (!dacc && K == 1 && !TA && !TB && !bias) {                  // outer product of a column and a row
+    g_outer1<<<g_blocks((int64_t)M * N), 256, 0, st>>>(M, N, A, lda, B, C, ldc); return;
+  }
+  if (dacc && M == 1 && TA && !TB) {                             // weighted column sums into the fp64 accumulators
+    g_wcolsum<<<dim3((n_valid + 127) / 128, (K + 63) / 64), 128, 0, st>>>(K, N, n_valid, A, lda, B, ldb, dacc); return;
+  }
   const bool aligned = !(lda & 3) && !(ldb & 3) && !((uintptr_t)A & 15) && !((uintptr_t)B & 15) &&
                        (TA ? !(M & 3) : !(K & 3)) && (TB ? !(K & 3) : !(N & 3));
   const bool big = M >= 64 && N >= 16 && K >= 32 && (double)M * N * K >= 4.0e6;

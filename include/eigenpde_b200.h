@@ -62,7 +62,8 @@ enum {
 #define EPDE_FLAG_SORT 1u     /* sort_eigvals_in_training (src/pytorch_eigen_solver.py:217-221) */
 #define EPDE_FLAG_DETERMINISTIC 2u  /* bit-identical gradients run to run: the tensor-core kernels then add tile
                                      contributions in a fixed order (costs ~7 % of the step); the FFMA2 kernels
-                                     and the generic path always are */
+                                     always are; the generic path adds its fp64 partials with atomics (order-
+                                     dependent only at the 1e-16 level, invisible after the fp32 conversion) */
 
 typedef struct epde_desc {
   int32_t d;                            /* input dimension n_0 (data_set.tot_dim) */
