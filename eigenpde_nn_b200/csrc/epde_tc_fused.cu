@@ -24,9 +24,19 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
   const size_t smem = ((size_t)TL.total() + (size_t)TG * TXR * 128) * 4 + 64;
-  cudaError_t e = cudaFuncSetAttribute(k_pass1_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_pass1_tc<<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);
+  cudaError_t e = cudaSuccess;
+#define EPDE_P1_LAUNCH(DC)                                                                                 \
+  do {                                                                                                     \
+    e = cudaFuncSetAttribute(k_pass1_tc<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return (int)e;                                                                   \
+    k_pass1_tc<DC><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);          \
+  } while (0)
+  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  if (std_pad && d == 50) EPDE_P1_LAUNCH(50);
+  else if (std_pad && d == 30) EPDE_P1_LAUNCH(30);
+  else if (std_pad && d == 2) EPDE_P1_LAUNCH(2);
+  else EPDE_P1_LAUNCH(0);
+#undef EPDE_P1_LAUNCH
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   int g2 = (int)((B + 255) / 256); if (g2 > nsm) g2 = nsm;
   switch (k) {
@@ -49,9 +59,20 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   if ((int64_t)gx * P2G > nt128) gx = (int)((nt128 + P2G - 1) / P2G);
   const int gn = GradLayout<TH>(d_pad).total();
   const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2_ACC2 * 4 + 128;
-  cudaError_t e = cudaFuncSetAttribute(k_pass2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_pass2_tc<<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order);
+  cudaError_t e = cudaSuccess;
+  // the BASELINE shapes get a compile-time d (no per-column predicates in the x handling); everything else DC = 0
+#define EPDE_P2_LAUNCH(DC)                                                                                          \
+  do {                                                                                                              \
+    e = cudaFuncSetAttribute(k_pass2_tc<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    k_pass2_tc<DC><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order); \
+  } while (0)
+  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  if (std_pad && d == 50) EPDE_P2_LAUNCH(50);
+  else if (std_pad && d == 30) EPDE_P2_LAUNCH(30);
+  else if (std_pad && d == 2) EPDE_P2_LAUNCH(2);
+  else EPDE_P2_LAUNCH(0);
+#undef EPDE_P2_LAUNCH
   *gx_out = gx;
   return (int)cudaGetLastError();
 }

@@ -271,10 +271,14 @@ __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, cons
 // k_pass1_tc: forward + Jacobian chain + energy for ONE net per CTA (blockIdx.y), 128-sample tiles
 //   part[(net * gridDim.x + blockIdx.x) * 2 + {0,1}] = sum w y, sum w e  (fp64);   ybuf[n][k]
 // ---------------------------------------------------------------------------------------------
+// DC > 0: input dimension known at compile time (see k_pass2_tc)
+template <int DC>
 __global__ void __launch_bounds__(TTHREADS, 1)
-k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad, int K,
+k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
            const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part) {
   constexpr int H = TH;
+  const int d = DC > 0 ? DC : d_rt;
+  const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
   extern __shared__ __align__(1024) unsigned char tsm[];
   const TcPack L(d);
   float* sw = reinterpret_cast<float*>(tsm);
