@@ -1,4 +1,5 @@
 // Launchers of the tensor-core fused family (separate translation unit: these kernels are large).
+#include <stdlib.h>
 #include "epde_tc_api.h"
 #include "epde_tc_fused.cuh"
 #include "epde_tc_pass2.cuh"
@@ -31,7 +32,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
     if (e != cudaSuccess) return (int)e;                                                                   \
     k_pass1_tc<DC><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);          \
   } while (0)
-  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  const bool std_pad = d_pad == (d + 3) / 4 * 4 && !getenv("EPDE_TC_GENERIC_D");
   if (std_pad && d == 50) EPDE_P1_LAUNCH(50);
   else if (std_pad && d == 30) EPDE_P1_LAUNCH(30);
   else if (std_pad && d == 2) EPDE_P1_LAUNCH(2);
@@ -67,7 +68,7 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
     if (e != cudaSuccess) return (int)e;                                                                            \
     k_pass2_tc<DC><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order); \
   } while (0)
-  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  const bool std_pad = d_pad == (d + 3) / 4 * 4 && !getenv("EPDE_TC_GENERIC_D");    // (dev knob: force DC = 0)
   if (std_pad && d == 50) EPDE_P2_LAUNCH(50);
   else if (std_pad && d == 30) EPDE_P2_LAUNCH(30);
   else if (std_pad && d == 2) EPDE_P2_LAUNCH(2);

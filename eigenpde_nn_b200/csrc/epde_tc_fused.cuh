@@ -141,6 +141,30 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// The x columns of one sample, xv[j] = x_j (j < d), 1 (j == d: the ones column of the folded bias), 0 beyond, for
+// j < 8 * ks1.  Whole 8-column chunks below d are loaded without per-column tests (the chunk tests are uniform over the
+// CTA); only the chunk that contains d pays for predicates.  `col` points at this thread's x_0, stride in floats.
+__device__ __forceinline__ void load_x_cols(float (&xv)[64], const float* __restrict__ col, int stride, int d, int ks1) {
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (c < ks1) {
+      if (8 * c + 8 <= d) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) xv[8 * c + i] = col[(size_t)(8 * c + i) * stride];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int j = 8 * c + i;
+          xv[j] = (j < d) ? col[(size_t)j * stride] : (j == d ? 1.f : 0.f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) xv[8 * c + i] = 0.f;
+    }
+  }
+}
+
 // ---- packed (f32x2) element-wise helpers over feature pairs: half the issue slots of the scalar forms ----------
 // tanh of two values + t = 1 - a^2 (FMUL2, 2 x EX2, FADD2, 2 x RCP, FFMA2, FFMA2)
 __device__ __forceinline__ void tanh_pair(float z0, float z1, float& a0, float& a1, float& t0, float& t1) {
@@ -345,8 +369,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     {
       float xv[64];
       mbar_wait(xbar, xph); xph ^= 1;
-#pragma unroll
-      for (int j = 0; j < 64; j++) xv[j] = (j < d) ? xs[j * 128] : (j == d ? 1.f : 0.f);
+      load_x_cols(xv, xs, 128, d, ks1);
       TC_ADD(6);
 #pragma unroll
       for (int c = 0; c < 8; c++) {

@@ -223,8 +223,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     // ---- S0: x -> A -------------------------------------------------------------------------------
     {
       float xv[64];
-#pragma unroll
-      for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
+      load_x_cols(xv, xcol, 128, d, ks1);
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         if (c < ks1) {
@@ -366,14 +365,18 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     tm_ld20(tl + dcol, z);
     {
       float xv[64];
-#pragma unroll
-      for (int j = 0; j < 64; j++) xv[j] = (j < d) ? __ldg(xcol + (size_t)j * 128) : (j == d ? 1.f : 0.f);
+      load_x_cols(xv, xcol, 128, d, ks1);
       TC_ADD(9);
       const uint32_t T = acquire(2, turn_want);
 #pragma unroll
       for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
 #pragma unroll
-      for (int j = 0; j < 64; j++) if (j < K1) stage_val(sN, j, xv[j]);
+      for (int c = 0; c < 8; c++) {
+        if (c < ks1) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) stage_val(sN, 8 * c + i, xv[8 * c + i]);
+        }
+      }
       TC_ADD(7);
       flush3(); TC_ADD(6);
       EPDE_P2_ROUND_ISSUE(T, 2, issue_round_rt(ks1, tm + D3, sgb))
