@@ -26,17 +26,21 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
   const size_t smem = ((size_t)TL.total() + (size_t)TG * TXR * 128) * 4 + 64;
   cudaError_t e = cudaSuccess;
-#define EPDE_P1_LAUNCH(DC)                                                                                 \
+#define EPDE_P1_LAUNCH(...)                                                                                 \
   do {                                                                                                     \
-    e = cudaFuncSetAttribute(k_pass1_tc<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    e = cudaFuncSetAttribute(k_pass1_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                   \
-    k_pass1_tc<DC><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);          \
+    k_pass1_tc<__VA_ARGS__><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);          \
   } while (0)
-  const bool std_pad = d_pad == (d + 3) / 4 * 4 && !getenv("EPDE_TC_GENERIC_D");
-  if (std_pad && d == 50) EPDE_P1_LAUNCH(50);
-  else if (std_pad && d == 30) EPDE_P1_LAUNCH(30);
-  else if (std_pad && d == 2) EPDE_P1_LAUNCH(2);
-  else EPDE_P1_LAUNCH(0);
+  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  if (std_pad && d == 50) EPDE_P1_LAUNCH(7, 50);          // the BASELINE shapes: exact d at compile time
+  else if (std_pad && d == 30) EPDE_P1_LAUNCH(4, 30);
+  else if (std_pad && d == 2) EPDE_P1_LAUNCH(1, 2);
+  else switch (TL.ks1) {   // any other d <= 63: one instantiation per layer-1 k-step count
+    case 1: EPDE_P1_LAUNCH(1); break;  case 2: EPDE_P1_LAUNCH(2); break;  case 3: EPDE_P1_LAUNCH(3); break;
+    case 4: EPDE_P1_LAUNCH(4); break;  case 5: EPDE_P1_LAUNCH(5); break;  case 6: EPDE_P1_LAUNCH(6); break;
+    case 7: EPDE_P1_LAUNCH(7); break;  default: EPDE_P1_LAUNCH(8); break;
+  }
 #undef EPDE_P1_LAUNCH
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   int g2 = (int)((B + 255) / 256); if (g2 > nsm) g2 = nsm;
@@ -61,18 +65,21 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   const int gn = GradLayout<TH>(d_pad).total();
   const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2_ACC2 * 4 + 128;
   cudaError_t e = cudaSuccess;
-  // the BASELINE shapes get a compile-time d (no per-column predicates in the x handling); everything else DC = 0
-#define EPDE_P2_LAUNCH(DC)                                                                                          \
+#define EPDE_P2_LAUNCH(...)                                                                                          \
   do {                                                                                                              \
-    e = cudaFuncSetAttribute(k_pass2_tc<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    e = cudaFuncSetAttribute(k_pass2_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return (int)e;                                                                            \
-    k_pass2_tc<DC><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order); \
+    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order); \
   } while (0)
-  const bool std_pad = d_pad == (d + 3) / 4 * 4 && !getenv("EPDE_TC_GENERIC_D");    // (dev knob: force DC = 0)
-  if (std_pad && d == 50) EPDE_P2_LAUNCH(50);
-  else if (std_pad && d == 30) EPDE_P2_LAUNCH(30);
-  else if (std_pad && d == 2) EPDE_P2_LAUNCH(2);
-  else EPDE_P2_LAUNCH(0);
+  const bool std_pad = d_pad == (d + 3) / 4 * 4;
+  if (std_pad && d == 50) EPDE_P2_LAUNCH(7, 50);
+  else if (std_pad && d == 30) EPDE_P2_LAUNCH(4, 30);
+  else if (std_pad && d == 2) EPDE_P2_LAUNCH(1, 2);
+  else switch (TL.ks1) {
+    case 1: EPDE_P2_LAUNCH(1); break;  case 2: EPDE_P2_LAUNCH(2); break;  case 3: EPDE_P2_LAUNCH(3); break;
+    case 4: EPDE_P2_LAUNCH(4); break;  case 5: EPDE_P2_LAUNCH(5); break;  case 6: EPDE_P2_LAUNCH(6); break;
+    case 7: EPDE_P2_LAUNCH(7); break;  default: EPDE_P2_LAUNCH(8); break;
+  }
 #undef EPDE_P2_LAUNCH
   *gx_out = gx;
   return (int)cudaGetLastError();

@@ -201,6 +201,7 @@ __host__ __device__ inline int kmaj_off(int n, int k, int K) {
 struct TcPack {
   int ks1;                                   // k-steps of layer 1: 8 * ks1 >= d + 1 (ones column at index d)
   __host__ __device__ explicit TcPack(int d) : ks1((d + 1 + 7) / 8) {}
+  __host__ __device__ TcPack(int, int ks) : ks1(ks) {}               // from the k-step count (compile-time in the kernels)
   __host__ __device__ int K1() const { return 8 * ks1; }
   __host__ __device__ int W1f(int lo) const { return lo * TN * K1(); }                    // B[k=j][n=o] = W1[o][j], row d = b1
   __host__ __device__ int mat(int m, int lo) const { return 2 * TN * K1() + (2 * m + lo) * TN * TKH; }
@@ -295,16 +296,16 @@ __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, cons
 // k_pass1_tc: forward + Jacobian chain + energy for ONE net per CTA (blockIdx.y), 128-sample tiles
 //   part[(net * gridDim.x + blockIdx.x) * 2 + {0,1}] = sum w y, sum w e  (fp64);   ybuf[n][k]
 // ---------------------------------------------------------------------------------------------
-// DC > 0: input dimension known at compile time (see k_pass2_tc)
-template <int DC>
+// KSC = number of layer-1 k-steps (see k_pass2_tc)
+template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(TTHREADS, 1)
 k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
            const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part) {
   constexpr int H = TH;
-  const int d = DC > 0 ? DC : d_rt;
+  const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
   extern __shared__ __align__(1024) unsigned char tsm[];
-  const TcPack L(d);
+  const TcPack L(d, KSC);
   float* sw = reinterpret_cast<float*>(tsm);
   float* xs0 = sw + L.total() + (size_t)(threadIdx.x >> 7) * TXR * 128;    // this group's x block [j][128]
   const float* xs = xs0 + (threadIdx.x & 127);                             // this thread's column

@@ -70,18 +70,18 @@ __device__ __forceinline__ void issue_round_rt(int n8, uint32_t d_t, uint32_t sg
   }
 }
 
-// DC > 0: input dimension known at compile time (d = DC, d_pad = 4 ceil(DC / 4)) - removes the per-column predicates of
-// the x handling; DC = 0: any d <= 63.
-template <int DC>
+// KSC = number of layer-1 k-steps, 8 KSC >= d + 1 (1..8): a template parameter because every TMEM column offset, weight-
+// image offset and MMA count of the kernel derives from it - computed per use they cost 16 % of the kernel's time.
+template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(P2THREADS, 1)
 k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
            const float* __restrict__ pwt, const float* __restrict__ ybuf, const Coef* __restrict__ coef,
            float* __restrict__ pg, int fixed_order) {
   constexpr int H = TH;
-  const int d = DC > 0 ? DC : d_rt;
+  const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
   extern __shared__ __align__(1024) unsigned char tsm[];
-  const TcPack L(d);
+  const TcPack L(d, KSC);
   const GradLayout<H> G(d_pad);
   const int gn = G.total();
   unsigned char* sg = tsm;                                          // staging buffer (SG_BYTES)
