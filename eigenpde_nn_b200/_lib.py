@@ -17,11 +17,13 @@ ACT_IDS = {"Tanh": 0, "Sigmoid": 1, "Softplus": 2, "LogSigmoid": 3, "ELU": 4, "C
            "Tanhshrink": 6}
 FLAG_SORT = 1
 FLAG_DETERMINISTIC = 2
+FLAG_FFMA2 = 4          # fused path: FP32 FFMA2 kernel family instead of the tcgen05 family (include/eigenpde_b200.h)
+ABI_VERSION = 3
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
            "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
-           "epde_eig_stats_accumulate", "epde_set_fused_impl", "epde_md_align", "epde_train_epilogue", "epde_peer_allreduce"]
+           "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_peer_allreduce"]
 
 
 class EpdeDesc(C.Structure):
@@ -61,7 +63,6 @@ def lib():
         L.epde_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, i64, vp]
         L.epde_average_accumulate.argtypes = [dp, vp, vp, vp, vp]
         L.epde_eig_stats_accumulate.argtypes = [dp, vp, vp, vp]
-        L.epde_set_fused_impl.argtypes = [C.c_int]
         L.epde_peer_allreduce.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, vp, vp, i64, C.c_int, i64, vp]
         L.epde_train_epilogue.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.epde_md_align.argtypes = [i64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp]
@@ -77,7 +78,20 @@ def check(rc: int, what: str):
         raise EpdeError("%s failed: %d (%s)" % (what, rc, lib().epde_error_string(rc).decode()))
 
 
-def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, metric_ptr=None) -> EpdeDesc:
+def activation_id(activation_name) -> int:
+    """The reference resolves `getattr(torch.nn, name)` and falls back to CELU only when torch.nn has no such attribute
+    (src/network_arch.py:27-32).  A torch.nn activation that exists but has no kernel here is an ERROR, never a silent
+    substitution: the host MyNet / the saved checkpoints would use the real activation while the step trained CELU."""
+    if activation_name in ACT_IDS:
+        return ACT_IDS[activation_name]
+    import torch
+    if getattr(torch.nn, str(activation_name), None) is None:
+        return ACT_IDS["CELU"]
+    raise EpdeError("activation torch.nn.%s exists but the step kernels implement only %s (EPDE_ERR_UNSUPPORTED)"
+                    % (activation_name, sorted(ACT_IDS)))
+
+
+def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, metric_ptr=None, ffma2=False) -> EpdeDesc:
     """arch = [d, n_1, ..., n_{L-1}, 1] (src/pytorch_eigen_solver.py:352)."""
     if len(arch) - 1 > EPDE_MAX_LAYERS:
         raise EpdeError("too many layers")
@@ -85,8 +99,7 @@ def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, m
     D.d, D.d_pad, D.k, D.n_layers = int(arch[0]), int(d_pad), int(k), len(arch) - 1
     for i, n in enumerate(arch):
         D.widths[i] = int(n)
-    # unknown activation names fall back to CELU in the reference (src/network_arch.py:27-32)
-    D.act_id = ACT_IDS.get(activation_name, ACT_IDS["CELU"])
-    D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0)
+    D.act_id = activation_id(activation_name)
+    D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0) | (FLAG_FFMA2 if ffma2 else 0)
     D.metric = metric_ptr
     return D

@@ -18,10 +18,9 @@ namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
 constexpr int kFusedH = 20;
-// family used by the last epde_step_partial on a workspace: epde_step_finish on the same workspace follows it even if
-// epde_set_fused_impl was called in between (the two phases share workspace layouts)
-struct { const void* ws; int impl; } g_last_partial = {nullptr, 1};
-int g_fused_impl = 1;                  // 1: tcgen05 kernels (epde_tc_fused.cuh, default)   0: FFMA2 kernels (epde_fused.cuh)
+// kernel family of the fused path: EPDE_FLAG_FFMA2 in the descriptor selects the FFMA2 kernels (epde_fused.cuh), the
+// default are the tcgen05 kernels (epde_tc_fused.cuh).  The choice travels with the descriptor: no process-wide state.
+inline int fused_impl(const epde_desc* D) { return (D->flags & EPDE_FLAG_FFMA2) ? 0 : 1; }
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
@@ -45,6 +44,7 @@ bool fused_ok(const epde_desc* D) {
   if (D->n_layers != 4 || D->act_id != EPDE_ACT_TANH) return false;
   if (D->widths[1] != kFusedH || D->widths[2] != kFusedH || D->widths[3] != kFusedH) return false;
   if (D->k > 6) return false;
+  if (D->d + 1 > 8 * 8) return false;           // tensor-core family: layer-1 k-steps 8 ks1 >= d + 1 with ks1 <= 8 (x staging rows TXR = 64)
   return pass2_smem_bytes<kFusedH>(D->d, D->d_pad) <= 227 * 1024 &&
          (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + 4096 <= 200 * 1024;
 }
@@ -60,6 +60,7 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 // ---- workspace ------------------------------------------------------------------------------
 struct FusedWs {
   float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
+  float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh)
   size_t total;
 };
 FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
@@ -75,6 +76,8 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.wt = (float*)take(ntl * GT * 4);
   W.pwt = (float*)take((size_t)D->k * tc::pack_floats(D->d) * 4);
   W.part2 = (double*)take((size_t)kMaxCtas * 32 * 8);
+  W.mx = (float*)take((size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4);
+  W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
   W.total = off;
   return W;
 }
@@ -109,12 +112,12 @@ cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt
 
 // gather + transpose the minibatch rows into the tile-major copy (workspace xt / wt)
 cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
-                          float* xt, float* wt, cudaStream_t st, int tile128 = 0) {
+                          float* xt, float* wt, cudaStream_t st, int tile128 = 0, float* mx = nullptr) {
   if (tile128) {     // tensor-core family: 128-sample tiles, wt padded to whole 256-sample tiles by the workspace layout
     const size_t sm1 = (size_t)128 * (D->d_pad + 1) * 4;
     cudaError_t e1 = cudaFuncSetAttribute(k_gather128<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     if (e1 != cudaSuccess) return e1;
-    k_gather128<0><<<(unsigned)((B + 127) / 128), 256, sm1, st>>>(X, w, idx, B, D->d_pad, xt, wt);
+    k_gather128<0><<<(unsigned)((B + 127) / 128), 256, sm1, st>>>(X, w, idx, B, D->d_pad, xt, wt, mx);
     return cudaGetLastError();
   }
   const size_t smem = (size_t)GT * (D->d_pad + 1) * 4;
@@ -128,13 +131,18 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
                   const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
-  const int impl = g_fused_impl;
-  g_last_partial.ws = ws; g_last_partial.impl = impl;
+  const int impl = fused_impl(D);
+  cudaError_t e;
   if (impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
-  cudaError_t e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1);
+  else {
+    e = cudaMemsetAsync(W.mx, 0, (size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4, st);     // maxima are gathered with atomicMax
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
   if (e != cudaSuccess) return (int)e;
   if (impl == 1)
-    return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums, st);
+    return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
+                       W.mx, W.nrm, st);
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
@@ -157,11 +165,12 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
                  const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
-  k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef);
-  if ((g_last_partial.ws == ws ? g_last_partial.impl : g_fused_impl) == 1) {
+  const int impl = fused_impl(D);
+  k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef,
+                              impl == 1 ? W.mx : nullptr, impl == 1 ? W.nrm : nullptr);
+  if (impl == 1) {
     int gx = 0;
-    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx,
-                    (D->flags & EPDE_FLAG_DETERMINISTIC) ? 1 : 0, st);
+    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx, st);
     if (rc) return rc;
     const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
     k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
@@ -483,12 +492,6 @@ int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* X, con
   }
   k_md_align<<<(unsigned)K, 64, 0, (cudaStream_t)stream>>>(X, K, n_atoms, d_pad, ref, diag, Xa, metric);
   return (int)cudaGetLastError();
-}
-
-int epde_set_fused_impl(int impl) {
-  if (impl != 0 && impl != 1) return EPDE_ERR_ARG;
-  g_fused_impl = impl;
-  return EPDE_OK;
 }
 
 int epde_train_epilogue(const epde_desc* D, float* params, const float* grad, float* m, float* v, double* state,

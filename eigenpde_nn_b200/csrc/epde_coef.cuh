@@ -9,7 +9,20 @@ struct Coef {                      // written by k_coef, read by k_pass2
   float ecoef[8];                  // ebar_{n,i} = w_n * ecoef[i]
   float cm[8];                     // ybar_{n,i} = w_n * (sum_j Cw[i][j] y_{n,j} - cm[i])
   float Cw[8][8];
+  // tensor-core family, fp16 gradient rounds: power-of-two staging scales per net and vector type
+  //   [0] g2  [1] g3  [2] ebar g1  [3] ubar1  [4] ubar2  [5] g1  [6] zbar2  [7] zbar3  [8] s4  [9] ybar  [10] a / 1
+  //   [11] zbar1  [12] x / 1
+  // and the factors that undo them when an accumulator block is added to the gradient image
+  //   [0..2] round 1 blocks  [3] zbar2 x a1  [4] zbar3 x a2  [5] s4 x 1  [6] ybar x 1  [7] zbar1 x x
+  float sc[8][16];
+  float fl[8][8];
 };
+
+// Bounds for the tensor-core family's fp16 staging (all device pointers, fp32):
+//   mx[0] = max w over the minibatch, mx[1] = max |x|, mx[2 + 4 net + {0: |g2|, 1: |g1|, 2: |K g1|, 3: |y|}]  (as float bits,
+//   written with atomicMax by k_gather128 / k_pass1_tc), nrm[8 net + {0: |W2|_inf, 1: |W2^T|_inf, 2: |W3|_inf,
+//   3: |W3^T|_inf, 4: max |w4|}] (k_pack_tc)
+constexpr int kMxPerNet = 4, kNrmPerNet = 8;
 
 
 struct EigW { double v[EPDE_MAX_K]; };
@@ -19,7 +32,8 @@ struct EigW { double v[EPDE_MAX_K]; };
 // reverse pass (SURVEY.md 8(a) closed form).  One thread; k <= 8.
 template <int DUMMY = 0>
 __global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
-                       double* __restrict__ out, Coef* __restrict__ coef) {
+                       double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx = nullptr,
+                       const float* __restrict__ nrm = nullptr) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double W = sums[0];
   const double* S1 = sums + 1;
@@ -71,6 +85,39 @@ __global__ void k_coef(const double* __restrict__ sums, int k, double beta, doub
         cmi += c / W * m[j];
       }
       coef->cm[i] = (float)cmi;
+    }
+    if (mx && nrm) {
+      // a-priori bounds of every vector the gradient rounds stage (per net), from the measured maxima of the forward /
+      // Jacobian quantities and the induced infinity norms of the weight matrices; 5 % slack for fp32 rounding
+      auto pow2 = [](double bound) -> double {        // s = 2^e with bound * s <= 2^14
+        if (!(bound > 0.0) || !isfinite(bound)) return 1.0;
+        int e; frexp(bound * 1.05, &e);
+        int q = 14 - e; q = q > 60 ? 60 : (q < -60 ? -60 : q);
+        return ldexp(1.0, q);
+      };
+      const double wmax = mx[0], xmax = fmax((double)mx[1], 1.0);
+      for (int i = 0; i < k; i++) {
+        const float* M = mx + 2 + kMxPerNet * i;
+        const float* N = nrm + kNrmPerNet * i;
+        const double g2m = M[0], g1m = M[1], tm = M[2], g3m = N[4];
+        const double nW2 = N[0], nW2T = N[1], nW3 = N[2], nW3T = N[3];
+        const double emax = wmax * fabs((double)coef->ecoef[i]);
+        double Y = fabs((double)coef->cm[i]);
+        for (int j = 0; j < k; j++) Y += fabs((double)coef->Cw[i][j]) * (double)mx[2 + kMxPerNet * j + 3];
+        Y *= wmax;
+        const double U1 = 2.0 * emax * tm, GB2 = nW2 * U1, GB3 = nW3 * GB2;
+        const double S4 = Y + GB3, Z3 = g3m * (2.0 * GB3 + Y);
+        const double Z2 = nW3T * Z3 + 2.0 * g2m * GB2, Z1 = nW2T * Z2 + 2.0 * g1m * U1;
+        double s[13];
+        s[0] = pow2(g2m); s[1] = pow2(g3m); s[2] = pow2(emax * g1m); s[3] = pow2(U1); s[4] = pow2(GB2); s[5] = pow2(g1m);
+        s[6] = pow2(Z2); s[7] = pow2(Z3); s[8] = pow2(S4); s[9] = pow2(Y); s[10] = 16384.0; s[11] = pow2(Z1);
+        s[12] = pow2(xmax);
+        for (int q = 0; q < 16; q++) coef->sc[i][q] = q < 13 ? (float)s[q] : 1.f;
+        coef->fl[i][0] = (float)(1.0 / (s[0] * s[3])); coef->fl[i][1] = (float)(1.0 / (s[1] * s[4]));
+        coef->fl[i][2] = (float)(1.0 / (s[2] * s[5])); coef->fl[i][3] = (float)(1.0 / (s[6] * s[10]));
+        coef->fl[i][4] = (float)(1.0 / (s[7] * s[10])); coef->fl[i][5] = (float)(1.0 / (s[8] * s[10]));
+        coef->fl[i][6] = (float)(1.0 / (s[9] * s[10])); coef->fl[i][7] = (float)(1.0 / (s[11] * s[12]));
+      }
     }
   }
 }

@@ -145,18 +145,21 @@ k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256)
 k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
-            int d_pad, float* __restrict__ xt, float* __restrict__ wt) {
+            int d_pad, float* __restrict__ xt, float* __restrict__ wt, float* __restrict__ mx) {
   extern __shared__ float4 smem4[];
   float* ts = reinterpret_cast<float*>(smem4);           // [128][d_pad + 1]
   __shared__ int64_t srow[128];
   const int ld = d_pad + 1, nq = d_pad >> 2, t = threadIdx.x;
   const int64_t tile = blockIdx.x;
+  float mw = 0.f, mxv = 0.f;                               // max w, max |x| of the minibatch (bounds of phase 2's fp16 staging)
   if (t < 128) {
     const int64_t n = tile * 128 + t;
     const bool v = n < B;
     const int64_t r = v ? (idx ? idx[n] : n) : 0;
     srow[t] = v ? r : -1;
-    wt[n] = v ? (w ? w[r] : 1.f) : 0.f;
+    const float wv = v ? (w ? w[r] : 1.f) : 0.f;
+    wt[n] = wv;
+    mw = fabsf(wv);
   }
   __syncthreads();
 #pragma unroll 4
@@ -167,8 +170,20 @@ k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int6
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     float* dst = ts + row * ld + 4 * q;
     dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
+    mxv = fmaxf(fmaxf(mxv, fmaxf(fabsf(val.x), fabsf(val.y))), fmaxf(fabsf(val.z), fabsf(val.w)));
+  }
+  __shared__ uint32_t smx[8][2];
+  if (mx) {
+    const uint32_t r0 = __reduce_max_sync(0xffffffffu, __float_as_uint(mw)), r1 = __reduce_max_sync(0xffffffffu, __float_as_uint(mxv));
+    if ((t & 31) == 0) { smx[t >> 5][0] = r0; smx[t >> 5][1] = r1; }
   }
   __syncthreads();
+  if (mx && t < 2) {      // one atomic per CTA and quantity, and only while the running maximum still grows (same-address atomics serialise in L2)
+    uint32_t v = 0;
+    for (int q = 0; q < 8; q++) v = max(v, smx[q][t]);
+    uint32_t* m = reinterpret_cast<uint32_t*>(mx) + t;
+    if (v > *reinterpret_cast<volatile uint32_t*>(m)) atomicMax(m, v);
+  }
   float* out = xt + (size_t)tile * d_pad * 128 + (t & 127);
   for (int j = (t >> 7); j < d_pad; j += 2) out[(size_t)j * 128] = ts[(t & 127) * ld + j];
 }

@@ -17,8 +17,8 @@
 
 namespace epde {
 
-// CTAs a split-K weight-gradient GEMM is cut into (dev knob EPDE_TC_SPLIT; 3 CTAs of g_gemm_tc fit on one SM)
-static int g_tc_split_target = -1;
+// CTAs a split-K weight-gradient GEMM is cut into (2 x 148: 3 CTAs of g_gemm_tc fit on one SM)
+constexpr int kTcSplitTarget = 296;
 
 // ---- activations: value, first and second derivative as functions of z ----------------------
 // torch.nn defaults (ELU/CELU alpha = 1, Softplus beta = 1 threshold = 20)
@@ -406,8 +406,7 @@ inline void gemm(cudaStream_t st, const TcCtx& tc, int M, int N, int K, const fl
       g_gemm_tc<TA, TB><<<dim3(nt, mt, 1), TC_THREADS, TC_SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, K, 0);
     } else {
       // split K over enough CTAs to fill the chip; partial tiles in fp32, summed into fp64 afterwards
-      if (g_tc_split_target < 0) { const char* e_ = getenv("EPDE_TC_SPLIT"); g_tc_split_target = (e_ && atoi(e_) > 0) ? atoi(e_) : 296; }
-      int nz = (g_tc_split_target + mt * nt - 1) / (mt * nt);
+      int nz = (kTcSplitTarget + mt * nt - 1) / (mt * nt);
       const int maxz = (K + 255) / 256;
       if (nz > maxz) nz = maxz;
       if (nz > 128) nz = 128;

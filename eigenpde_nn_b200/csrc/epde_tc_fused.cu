@@ -18,9 +18,10 @@ namespace tc {
 size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
 
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
-            const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, cudaStream_t st) {
+            const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
+            cudaStream_t st) {
   const TcPack TL(d);
-  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt);
+  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
@@ -30,7 +31,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
   do {                                                                                                     \
     e = cudaFuncSetAttribute(k_pass1_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                   \
-    k_pass1_tc<__VA_ARGS__><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part);          \
+    k_pass1_tc<__VA_ARGS__><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part, mx);      \
   } while (0)
   const bool std_pad = d_pad == (d + 3) / 4 * 4;
   if (std_pad && d == 50) EPDE_P1_LAUNCH(7, 50);          // the BASELINE shapes: exact d at compile time
@@ -57,19 +58,19 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 }
 
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
-           const float* ybuf, const Coef* coef, float* pg, int* gx_out, int fixed_order, cudaStream_t st) {
+           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st) {
   const TcPack TL(d);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * P2G > nt128) gx = (int)((nt128 + P2G - 1) / P2G);
   const int gn = GradLayout<TH>(d_pad).total();
-  const size_t smem = (size_t)SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2_ACC2 * 4 + 128;
+  const size_t smem = (size_t)P2G * SG_BYTES + (size_t)TL.total() * 4 + (size_t)P2G * im_total(TL.K1()) * 4 + 768;
   cudaError_t e = cudaSuccess;
 #define EPDE_P2_LAUNCH(...)                                                                                          \
   do {                                                                                                              \
     e = cudaFuncSetAttribute(k_pass2_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return (int)e;                                                                            \
-    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg, fixed_order); \
+    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg);      \
   } while (0)
   const bool std_pad = d_pad == (d + 3) / 4 * 4;
   if (std_pad && d == 50) EPDE_P2_LAUNCH(7, 50);

@@ -213,7 +213,7 @@ struct TcPack {
 
 // one CTA per net: flat parameters -> TcPack image in global memory (hi / lo split done here, once per step)
 __global__ void k_pack_tc(const float* __restrict__ params, const float* __restrict__ diag_coeff, int d,
-                          float* __restrict__ pwt) {
+                          float* __restrict__ pwt, float* __restrict__ nrm) {
   constexpr int H = TH;
   const TcPack L(d);
   const int net = blockIdx.x, K1 = L.K1();
@@ -253,6 +253,20 @@ __global__ void k_pack_tc(const float* __restrict__ params, const float* __restr
   }
   for (int e = threadIdx.x; e < TKH + 8; e += blockDim.x)
     o[L.w4() + e] = (e < H) ? W4[e] : (e == TKH ? b4[0] : 0.f);
+  // induced infinity norms for the bounds of phase 2's fp16 staging (k_coef): max row / column abs sums, max |w4|
+  __shared__ float sn[5][H];
+  if (threadIdx.x < H) {
+    const int r = threadIdx.x;
+    float a = 0.f, b = 0.f, c = 0.f, e = 0.f;
+    for (int i = 0; i < H; i++) { a += fabsf(W2[r * H + i]); b += fabsf(W2[i * H + r]); c += fabsf(W3[r * H + i]); e += fabsf(W3[i * H + r]); }
+    sn[0][r] = a; sn[1][r] = b; sn[2][r] = c; sn[3][r] = e; sn[4][r] = fabsf(W4[r]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float m = 0.f;
+    for (int i = 0; i < H; i++) m = fmaxf(m, sn[threadIdx.x][i]);
+    nrm[kNrmPerNet * net + threadIdx.x] = m;
+  }
 }
 
 // issue one 3xTF32 mat-vec chain: D[128 x 32] = A[128 x 8 KS] * B, small terms first (the accumulator truncates).
@@ -300,7 +314,7 @@ __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, cons
 template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(TTHREADS, 1)
 k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
-           const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part) {
+           const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part, float* __restrict__ mx) {
   constexpr int H = TH;
   const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
@@ -346,6 +360,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   uint64_t* bar = bars + g;
   uint32_t ph = 0;
   double accS = 0.0, accE = 0.0;
+  float mg2 = 0.f, mg1 = 0.f, mt = 0.f, my = 0.f;      // running maxima of |g2|, |g1|, |K g1|, |y| (bounds of phase 2's fp16 staging)
   TC_DECL();
 
   const int64_t nt128 = (B + 127) / 128;
@@ -428,18 +443,23 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
     for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t2[i], t2[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g2
+#pragma unroll
+    for (int i = 0; i < H; i += 2) mg2 = fmaxf(mg2, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(2))                                  // u1 = W2^T g2
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
     for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t1[i], t1[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g1
+#pragma unroll
+    for (int i = 0; i < H; i += 2) mg1 = fmaxf(mg1, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(4))                                  // K g1
     tm_ld20(tl + dcol, z); TC_ADD(5);
     float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < H; i += 2) { e0 = fmaf(v[i], z[i], e0); e1 = fmaf(v[i + 1], z[i + 1], e1); }
+    for (int i = 0; i < H; i += 2) { e0 = fmaf(v[i], z[i], e0); e1 = fmaf(v[i + 1], z[i + 1], e1); mt = fmaxf(mt, fmaxf(fabsf(z[i]), fabsf(z[i + 1]))); }
     const float e = e0 + e1;
+    my = fmaxf(my, fabsf(y));
 #undef EPDE_TC_STAGE
 #undef EPDE_TC_MV
     if (n < B) ybuf[n * K + net] = y;
@@ -455,6 +475,18 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     double v = 0.0;
     for (int q = 0; q < TTHREADS / 32; q++) v += red[q][tid];
     part[((size_t)net * gridDim.x + blockIdx.x) * 2 + tid] = v;
+  }
+  {  // maxima: non-negative floats order like their bit patterns
+    const uint32_t r0 = __reduce_max_sync(0xffffffffu, __float_as_uint(mg2)), r1 = __reduce_max_sync(0xffffffffu, __float_as_uint(mg1));
+    const uint32_t r2 = __reduce_max_sync(0xffffffffu, __float_as_uint(mt)), r3 = __reduce_max_sync(0xffffffffu, __float_as_uint(my));
+    if ((tid & 31) == 0) {
+      uint32_t* m = reinterpret_cast<uint32_t*>(mx) + 2 + kMxPerNet * net;
+      volatile uint32_t* mv = m;
+      if (r0 > mv[0]) atomicMax(m + 0, r0);
+      if (r1 > mv[1]) atomicMax(m + 1, r1);
+      if (r2 > mv[2]) atomicMax(m + 2, r2);
+      if (r3 > mv[3]) atomicMax(m + 3, r3);
+    }
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tm));
 }

@@ -1,20 +1,28 @@
 // k_pass2_tc: phase 2 of the fused step on the tensor cores (see epde_tc_fused.cuh for the conventions).
 //
 // Per 128-sample tile and net, thread = sample:
-//   mat-vec chain (TS-form MMAs, A in TMEM):  x -> a1 -> a2 -> a3 | g3 -> u2 | g2 -> u1 | g1 -> K g1 |
+//   mat-vec chain (TS-form tf32 MMAs, 3xTF32 split, A in TMEM):  x -> a1 -> a2 -> a3 | g3 -> u2 | g2 -> u1 | g1 -> K g1 |
 //       ubar1 -> gbar2 | ubar2 -> gbar3 | zbar3 -> W3^T zbar3 | zbar2 -> W2^T zbar2 -> zbar1
 //   weight gradients = contractions over the SAMPLES:  G[p][q] = sum_n P[n][p] Q[n][q]  (SS-form MMAs, M = 64):
-//       the P / Q vectors of a "round" are written by their threads into a shared staging buffer as K-major
-//       [feature][sample] images (hi / lo), several vectors stacked along M and along N:
+//       the P / Q vectors of a "round" are written by their threads into the group's staging buffer as K-major
+//       [feature][sample] images, several vectors stacked along M and along N:
 //         round 1:  M = [g2 | g3 | ebar g1]        N = [ubar1 | ubar2 | g1]      -> dW2 (g part), dW3 (g part), Gamma
 //         round 2:  M = [zbar2 | zbar3 | s4 | ybar] N = [a1 | 1 | a2 | 1]         -> dW2, db2, dW3, db3, dw4, db4
 //         round 3:  M = [zbar1]                     N = [x | 1]                   -> dW1 (z part), db1
-//   The two groups of a CTA share ONE staging buffer: rounds are serialised by a ticket, round T commits to
-//   ring[T % 4] and the holder of ticket T waits for round T-1 before it touches the buffer.  The accumulators of a
-//   round live in TMEM only for that round (the fp32 accumulator truncates, so nothing is accumulated across
-//   tiles there): the next holder of the same round type first adds them (round-to-nearest) into the per-CTA
-//   shared-memory gradient image.
+//
+// Round 2 of the build (measured on B200, tools/tc_test/f16_probe.cu, profiles/f16_probe_r2.txt):
+//   * the rounds run in kind::f16 with a TWO-term fp16 split  v * s = hi + lo  (s = a power of two per vector type that
+//     maps the vector's a-priori bound to 2^14, computed per step by k_coef from maxima measured in phase 1): hi * hi +
+//     hi * lo + lo * hi is as accurate as 3xTF32 (both 11-bit significands; measured 4.8e-5 vs 7.1e-5 abs. on sums of
+//     ~100), but one MMA covers 16 samples instead of 8 and an image is half the size: half the MMAs, half the
+//     shared-memory operand traffic, and TWO staging buffers fit - one per group;
+//   * an M = 64 accumulator occupies lanes 0-15 of every 32-lane quarter; a lane offset of 16 in the D address puts a
+//     second accumulator into the other half of the same columns, so each group owns private accumulators.
+//   Together: no ticket, no shared buffer, no cross-group synchronisation at all.  A group accumulates P2F tiles in
+//   TMEM, then adds the needed blocks (round-to-nearest) into its private shared-memory image; the two images are summed
+//   in a fixed order at the end, so the result is bit-identical run to run without a special mode.
 #pragma once
+#include <cuda_fp16.h>
 #include "epde_tc_fused.cuh"
 
 namespace epde {
@@ -22,52 +30,72 @@ namespace tc {
 
 constexpr int P2G = 2;                          // groups per CTA (long-lived per-sample state stays in registers)
 constexpr int P2THREADS = 128 * P2G;
-constexpr uint32_t SG_LBO = 144;                // bytes between 4-sample chunks of a staging row group (conflict-free STS.32)
-constexpr uint32_t SG_SBO = 32 * SG_LBO;        // bytes between 8-row groups (128 samples)
-constexpr int SG_ROWS = 64;                     // rows per image
-constexpr uint32_t SG_IMG = (SG_ROWS / 8) * SG_SBO;   // one image (hi or lo) = 36864 B
-// staging buffer: [M hi][M lo][N hi][N lo]
-constexpr uint32_t SG_BYTES = 4 * SG_IMG;
-constexpr int P2_S1 = 65, P2_S2 = 49, P2_S3 = 65;   // row strides of the raw accumulator images (odd: conflict-free)
-constexpr int P2_ACC2 = 64 * P2_S1 + 64 * P2_S2 + 20 * P2_S3;   // raw per-CTA accumulator images of the three round types
+constexpr int P2F = 1;                          // tiles accumulated in TMEM between flushes; must stay 1 while some staging scales are per-tile
+// staging images are MN-major, no swizzle: element (feature f, sample n) of an image at
+//   (f / 8) * SG_SMN + (n / 8) * 128 + (n % 8) * 16 + (f % 8) * 2   bytes,
+// a core matrix = 8 samples (K) x 8 features (contiguous 16 bytes); core matrices are contiguous along K, so a thread
+// (= sample) writes 8 features with ONE 16-byte store and a warp's stores are 512 contiguous bytes (conflict-free).
+// Descriptor: LBO = 128 (K direction), SBO = SG_SMN (measured: tools/tc_test/mn_probe.cu; the K-major layout of round 1
+// needed one 2-byte store per value and was bound by the LSU instruction rate).
+constexpr uint32_t SG_SMN = 16 * 128;           // bytes between 8-feature groups (128 samples)
+constexpr int SG_ROWS = 64;                     // features per image
+constexpr uint32_t SG_IMG = (SG_ROWS / 8) * SG_SMN;   // one image (hi or lo) = 16384 B
+constexpr uint32_t SG_BYTES = 4 * SG_IMG;       // one group's staging buffer: [M hi][M lo][N hi][N lo]
+// group-private gradient image (floats): W2 | b2, W3 | b3, Gamma with row stride 21, w4 | b4, W1 | b1 with row stride S3
+constexpr int IM_S = 21;
+constexpr int IM_W2 = 0, IM_W3 = 20 * IM_S, IM_G = 40 * IM_S, IM_W4 = 60 * IM_S, IM_W1 = IM_W4 + 24;
+__host__ __device__ constexpr int im_s3(int K1) { return K1 + 1; }                    // odd: conflict-free row-wise RMW
+__host__ __device__ constexpr int im_total(int K1) { return IM_W1 + 20 * im_s3(K1) + 4; }
 
-__device__ __forceinline__ void sts32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
-// write value v of staging row r (this thread's sample column) into the hi and lo images starting at img
-// (truncating split: hi = top 19 bits exactly as the MMA would read them, lo = x - hi exact; one instruction less
-//  per value than the round-to-nearest split of the mat-vec operands, same 3xTF32 accuracy to first order)
-__device__ __forceinline__ void stage_val(uint32_t img_hi, int r, float v) {
-  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u), lo = v - hi;
-  const uint32_t o = (uint32_t)(r >> 3) * SG_SBO + (uint32_t)(r & 7) * 16u;
-  sts32(img_hi + o, hi); sts32(img_hi + SG_IMG + o, lo);
+// Stage NCH chunks of 8 features of this thread's sample: get(r) returns the SCALED value of feature row r (r is a
+// compile-time constant after unrolling, so the selection inside `get` costs nothing).  v = hi + lo with fp16 hi, lo.
+template <int NCH, typename F>
+__device__ __forceinline__ void stage_rows(uint32_t img_hi, F get) {
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float x0 = get(8 * c + 2 * j), x1 = get(8 * c + 2 * j + 1);
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(x1), "f"(x0));       // x0 -> low half
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    }
+    sts128(img_hi + (uint32_t)c * SG_SMN, h); sts128(img_hi + SG_IMG + (uint32_t)c * SG_SMN, l);
+  }
 }
 
-// one gradient round: D[64 x N] = sum over 128 samples, 3xTF32, small terms first; fresh accumulator
+__device__ __forceinline__ constexpr uint32_t idesc_f16(int M, int N) {     // D fp32, A/B fp16, both MN-major (bits 15, 16)
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss16(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// one gradient round: D[64 x N] (+)= sum over 128 samples of (hi + lo)(hi + lo) without lo * lo, small terms first
 template <int N>
-__device__ __forceinline__ void issue_round(uint32_t d_t, uint32_t sg_base) {
-  const uint32_t idesc = idesc_tf32(64, N);
-  const uint64_t mh = kdesc(sg_base, SG_LBO, SG_SBO), ml = kdesc(sg_base + SG_IMG, SG_LBO, SG_SBO);
-  const uint64_t nh = kdesc(sg_base + 2 * SG_IMG, SG_LBO, SG_SBO), nl = kdesc(sg_base + 3 * SG_IMG, SG_LBO, SG_SBO);
+__device__ __forceinline__ void issue_round(uint32_t d_t, uint32_t sg_base, uint32_t accumulate) {
+  const uint32_t idesc = idesc_f16(64, N);
+  const uint64_t mh = kdesc(sg_base, 128, SG_SMN), ml = kdesc(sg_base + SG_IMG, 128, SG_SMN);
+  const uint64_t nh = kdesc(sg_base + 2 * SG_IMG, 128, SG_SMN), nl = kdesc(sg_base + 3 * SG_IMG, 128, SG_SMN);
 #pragma unroll
-  for (int ks = 0; ks < 16; ks++) {               // 8 samples per MMA = two 4-sample chunks = 288 B = 18 address units
-    mma_ss(d_t, ml + 18 * ks, nh + 18 * ks, idesc, ks ? 1u : 0u);
-    mma_ss(d_t, mh + 18 * ks, nl + 18 * ks, idesc, 1u);
+  for (int ks = 0; ks < 8; ks++) {                // 16 samples per MMA = two core matrices along K = 256 B = 16 address units
+    mma_ss16(d_t, ml + 16 * ks, nh + 16 * ks, idesc, ks ? 1u : accumulate);
+    mma_ss16(d_t, mh + 16 * ks, nl + 16 * ks, idesc, 1u);
   }
 #pragma unroll
-  for (int ks = 0; ks < 16; ks++) mma_ss(d_t, mh + 18 * ks, nh + 18 * ks, idesc, 1u);
+  for (int ks = 0; ks < 8; ks++) mma_ss16(d_t, mh + 16 * ks, nh + 16 * ks, idesc, 1u);
 }
-__device__ __forceinline__ void issue_round_rt(int n8, uint32_t d_t, uint32_t sg_base) {
-  switch (n8) {
-    case 1: issue_round<8>(d_t, sg_base); break;
-    case 2: issue_round<16>(d_t, sg_base); break;
-    case 3: issue_round<24>(d_t, sg_base); break;
-    case 4: issue_round<32>(d_t, sg_base); break;
-    case 5: issue_round<40>(d_t, sg_base); break;
-    case 6: issue_round<48>(d_t, sg_base); break;
-    case 7: issue_round<56>(d_t, sg_base); break;
-    default: issue_round<64>(d_t, sg_base); break;
-  }
+__device__ __forceinline__ void tm_ld8(uint32_t t, float* r) {
+  uint32_t v[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(t));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = __uint_as_float(v[i]);
 }
 
 // KSC = number of layer-1 k-steps, 8 KSC >= d + 1 (1..8): a template parameter because every TMEM column offset, weight-
@@ -76,7 +104,7 @@ template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(P2THREADS, 1)
 k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
            const float* __restrict__ pwt, const float* __restrict__ ybuf, const Coef* __restrict__ coef,
-           float* __restrict__ pg, int fixed_order) {
+           float* __restrict__ pg) {
   constexpr int H = TH;
   const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
@@ -84,21 +112,28 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   const TcPack L(d, KSC);
   const GradLayout<H> G(d_pad);
   const int gn = G.total();
-  unsigned char* sg = tsm;                                          // staging buffer (SG_BYTES)
-  float* sw = reinterpret_cast<float*>(tsm + SG_BYTES);             // packed weights
-  float* acc = reinterpret_cast<float*>(sg);                        // per-CTA gradient image (GradLayout): built at the END in the (then idle) staging buffer
-  float* acc2 = sw + L.total();                                     // raw accumulator images (see flush*)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(acc2 + P2_ACC2);     // [P2G] mat-vec, [4] round ring
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + P2G + 4);     // [0] tmem base, [1] ticket, [2..3] ticket of group, [4..6] turn of round type
+  constexpr int K1 = 8 * KSC, ks1 = KSC;
+  constexpr int S3 = im_s3(K1), IMT = im_total(K1);
+  unsigned char* sg = tsm;                                          // staging buffers (P2G * SG_BYTES)
+  float* sw = reinterpret_cast<float*>(tsm + P2G * SG_BYTES);       // packed weights
+  float* acc = reinterpret_cast<float*>(sg);                        // per-CTA gradient image (GradLayout): built at the END in the (then idle) staging buffers
+  float* imgs = sw + L.total();                                     // group-private gradient images
+  uint64_t* bars = reinterpret_cast<uint64_t*>(imgs + P2G * IMT);   // [P2G] mat-vec, [P2G] rounds
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * P2G);     // [0] tmem base
+  float* scs = reinterpret_cast<float*>(slot + 4);                  // [16] staging scales, [8] flush factors of this net
+  uint32_t* dynm = reinterpret_cast<uint32_t*>(scs + 32) + (threadIdx.x >> 7) * 32;   // this group's [8 vector types][4 warps] tile maxima (float bits)
   const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, wq = warp & 3, lane = tid & 31, net = blockIdx.y;
   const int sn = tid & 127;                                         // sample within the tile = TMEM lane
   {
     const float* src = pwt + (size_t)net * L.total();
     for (int i = tid; i < L.total(); i += P2THREADS) sw[i] = src[i];
-    for (int i = tid; i < P2_ACC2; i += P2THREADS) acc2[i] = 0.f;
-    for (uint32_t i = tid; i < SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
+    for (int i = tid; i < P2G * IMT; i += P2THREADS) imgs[i] = 0.f;
+    for (uint32_t i = tid; i < P2G * SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
+    if (tid < 16) scs[tid] = coef->sc[net][tid];
+    if (tid >= 32 && tid < 40) scs[16 + tid - 32] = coef->fl[net][tid - 32];
+    if (tid == 40) { scs[26] = 1.f / coef->sc[net][1]; scs[27] = 1.f / coef->sc[net][12]; }      // 1 / s(g3), 1 / s(x)
   }
-  if (tid == 0) { for (int i = 0; i < P2G + 4; i++) mbar_init(bars + i, 1); slot[1] = 0; slot[4] = 0; slot[5] = 0; slot[6] = 0; }
+  if (tid == 0) { for (int i = 0; i < 2 * P2G; i++) mbar_init(bars + i, 1); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -107,92 +142,108 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   fence_before(); __syncthreads(); fence_after();
   const uint32_t tm = slot[0];
-  const int K1 = L.K1(), ks1 = L.ks1;
-  const int KA = K1 > 56 ? K1 : 56;                                  // A region: x (K1 columns); hidden vectors use 24 of them,
+  constexpr int KA = K1 > 56 ? K1 : 56;                              // A region: x (K1 columns); hidden vectors use 24 of them,
   const uint32_t gc = (uint32_t)g * (2 * KA + TN);                   // columns 24..43 of the hi and lo halves park long-lived vectors
   const uint32_t tl = tm + ((uint32_t)(wq * 32) << 16);
   const uint32_t ahi = gc, alo = gc + KA, dcol = gc + 2 * KA;
   const uint32_t pkA = tl + ahi + 24, pkB = tl + alo + 24;           // parking slots (20 columns each)
-  const uint32_t gbase = (uint32_t)P2G * (2 * KA + TN);             // gradient accumulators: D1 (64), D2 (48), D3 (K1)
-  const uint32_t D1 = gbase, D2 = gbase + 64, D3 = gbase + 112;
-  {  // zero the accumulators once (the first flush of every round type adds them)
-    float zr[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) zr[i] = 0.f;
-    if (g == 0) { for (uint32_t c = 0; c < 112 + (uint32_t)K1; c += 16) tm_st16(tl + gbase + c, zr); wait_st(); }
-  }
+  constexpr uint32_t gbase = (uint32_t)P2G * (2 * KA + TN);          // gradient accumulators: D1 (64), D2 (48), D3 (K1); group g in lanes 16 g .. 16 g + 15
+  constexpr uint32_t D1 = gbase, D2 = gbase + 64, D3 = gbase + 112;
+  const uint32_t dlane = (uint32_t)(16 * g) << 16;                   // lane offset of this group's accumulators (MMA D address)
   const uint32_t idesc = idesc_tf32(128, TN);
-  const uint32_t sbase = smem_u32(sw), sgb = smem_u32(sg);
+  const uint32_t sbase = smem_u32(sw), sgb = smem_u32(sg) + (uint32_t)g * SG_BYTES;
   const float b4r = sw[L.b4()];
   const float ecoef = coef->ecoef[net], cm = coef->cm[net];
   uint64_t* bar = bars + g;
-  uint64_t* ring = bars + P2G;
-  uint32_t ph = 0;
+  uint64_t* rbar = bars + P2G + g;
+  uint32_t ph = 0, rph = 0;
+  float* img = imgs + g * IMT;
   TC_DECL();
-  // this thread's column inside a staging image
-  const uint32_t tcol = (uint32_t)(sn >> 2) * SG_LBO + (uint32_t)(sn & 3) * 4u;
-  const uint32_t sM = sgb + tcol, sN = sgb + 2 * SG_IMG + tcol;
-  fence_before(); __syncthreads(); fence_after();
+  // this thread's 16-byte slot inside a feature group of a staging image
+  const uint32_t sM = sgb + (uint32_t)sn * 16u, sN = sgb + 2 * SG_IMG + (uint32_t)sn * 16u;
+  // accumulator rows this thread reads back (M = 64 layout: row r in lane (r / 16) * 32 + r % 16, + 16 for group 1)
+  const bool frow_on = (lane >> 4) == g;
+  const int frow = 16 * wq + (lane & 15);
+  const int fblk = frow / 20, fi = frow - 20 * fblk;
 
-  // ---- flush of a round's accumulator (M = 64 layout: row r in lane (r / 16) * 32 + r % 16) into acc ----------
-  // Only the holder of the staging buffer runs this, so plain read-modify-write is safe; every chunk is
-  // load-all / add-all / store-all (a chain of dependent shared-memory RMWs costs ~60 cycles per element).
-  auto rmw16 = [&](float* p, const float* v, bool on) {      // p[0..15] += v[0..15]
+  // ---- dynamic staging scales ------------------------------------------------------------------------------------
+  // The backward vectors (ubar2, zbar3, zbar2, s4, zbar1) cancel heavily, so a-priori bounds overestimate them by up to
+  // 2^18 (MD-style weights, tests/golden/cfg3_md_30d_k2): their scale is taken from the tile's ACTUAL maximum instead.
+  // Every warp publishes max |v| over its 32 samples (float bits) before a group barrier the stage needs anyway; after
+  // it every thread derives the same power of two s with  2^13 <= s * max < 2^14.  fd[] keeps the factors that undo the
+  // scales of the tile whose accumulators are flushed next: [0] g3 x ubar2, [1] zbar2 x a, [2] zbar3 x a, [3] s4 x 1,
+  // [4] zbar1 x x.
+  float fd[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  auto publish_max = [&](int slot_id, const float (&v)[H]) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < H; i += 2) m = fmaxf(m, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+    const uint32_t r = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if (lane == 0) dynm[slot_id * 4 + wq] = r;
+  };
+  auto dyn_scale = [&](int slot_id, float& inv) -> float {          // after the group barrier that follows publish_max
+    const uint4 q = *reinterpret_cast<const uint4*>(dynm + slot_id * 4);
+    uint32_t e = max(max(q.x, q.y), max(q.z, q.w)) >> 23;            // biased exponent of the group maximum
+    e = e < 87u ? 87u : (e > 167u ? 167u : e);                       // scales within 2^-26 .. 2^54
+    inv = __uint_as_float((e - 13u) << 23);                          // 2^(e - 127 + 1 - 14)
+    return __uint_as_float((267u - e) << 23);                        // 2^(14 - (e - 127 + 1))
+  };
+  // ---- flush: add the needed blocks of a round's accumulator, un-scaled, into this group's image ---------------
+  auto rmw = [&](float* p, const float* v, int n, float f, bool on) {      // p[0..n) += f * v[0..n)   (n <= 21, compile-time after unrolling)
     if (on) {
-      float o[16];
+      float o[21];
 #pragma unroll
-      for (int i = 0; i < 16; i++) o[i] = p[i];
+      for (int i = 0; i < 21; i++) if (i < n) o[i] = p[i];
 #pragma unroll
-      for (int i = 0; i < 16; i++) p[i] = o[i] + v[i];
+      for (int i = 0; i < 21; i++) if (i < n) p[i] = fmaf(v[i], f, o[i]);
     }
   };
-  // acc image used while the kernel runs: the three accumulators verbatim, [row][col] with 64 / 48 / 64 columns
-  //   A1 = acc2 + 0, A2 = acc2 + 64 * 64, A3 = acc2 + 64 * 64 + 64 * 48
-  // two 16-column chunks per tcgen05.wait::ld
-  auto flush_rows = [&](uint32_t dcol0, float* base, int stride, int ncol, bool on) {
-    const int r = 16 * wq + lane;
-    float v[32];
+  auto flush1 = [&]() {      // rows g2 | g3 | ebar g1 against cols ubar1 | ubar2 | g1: the three diagonal 20 x 20 blocks
+    float w[40], x[20];
+    const uint32_t c0 = wq < 2 ? 0u : 20u;                           // warp-uniform 40-column window
+    tm_ld16(tl + D1 + c0, w); tm_ld16(tl + D1 + c0 + 16, w + 16); tm_ld8(tl + D1 + c0 + 32, w + 32); wait_ld();
+    const bool hi = (uint32_t)(20 * fblk) != c0;
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      if (c0 < ncol) {
-        tm_ld16(tl + dcol0 + c0, v);
-        if (c0 + 16 < ncol) tm_ld16(tl + dcol0 + c0 + 16, v + 16);
-        wait_ld();
-        rmw16(base + r * stride + c0, v, on);
-        if (c0 + 16 < ncol) rmw16(base + r * stride + c0 + 16, v + 16, on);
+    for (int i = 0; i < 20; i++) x[i] = hi ? w[20 + i] : w[i];
+    float* p = img + (fblk == 0 ? IM_W2 : (fblk == 1 ? IM_W3 : IM_G)) + fi * IM_S;
+    rmw(p, x, 20, fblk == 1 ? fd[0] : scs[16 + (fblk < 3 ? fblk : 0)], frow_on && fblk < 3);
+  };
+  auto flush2 = [&]() {      // rows zbar2 | zbar3 | s4 | ybar against cols a1 | 1 | a2 | 1
+    float w[48], x[21];
+    tm_ld16(tl + D2, w); tm_ld16(tl + D2 + 16, w + 16); tm_ld16(tl + D2 + 32, w + 32); wait_ld();
+#pragma unroll
+    for (int i = 0; i < 21; i++) x[i] = fblk == 1 ? w[21 + i] : w[i];
+    if (fblk < 2) {
+      rmw(img + (fblk == 0 ? IM_W2 : IM_W3) + fi * IM_S, x, 21, fblk == 0 ? fd[1] : fd[2], frow_on);
+    } else if (frow_on && frow <= 60) {
+      img[IM_W4 + frow - 40] = fmaf(w[20], frow < 60 ? fd[3] : scs[22], img[IM_W4 + frow - 40]);     // dw4[0..19], db4
+    }
+  };
+  auto flush3 = [&]() {      // rows zbar1 against cols x | 1
+    if (wq < 2) {
+      const bool on = frow_on && frow < 20;
+      const float f = fd[4];
+#pragma unroll
+      for (int c0 = 0; c0 < K1; c0 += 16) {
+        float w[16];
+        if (c0 + 16 <= K1) { tm_ld16(tl + D3 + c0, w); wait_ld(); rmw(img + IM_W1 + frow * S3 + c0, w, 16, f, on); }
+        else { tm_ld8(tl + D3 + c0, w); wait_ld(); rmw(img + IM_W1 + frow * S3 + c0, w, 8, f, on); }
       }
     }
   };
-  auto flush1 = [&]() { flush_rows(D1, acc2, P2_S1, 64, lane < 16); };                       // rows g2 | g3 | ebar g1, cols ubar1 | ubar2 | g1
-  auto flush2 = [&]() { flush_rows(D2, acc2 + 64 * P2_S1, P2_S2, 48, lane < 16); };          // rows zbar2 | zbar3 | s4 | ybar, cols a1 | 1 | a2 | 1
-  auto flush3 = [&]() { flush_rows(D3, acc2 + 64 * P2_S1 + 64 * P2_S2, P2_S3, K1, lane < 16 && 16 * wq + lane < 20); };   // rows zbar1, cols x | 1
-  // take the staging buffer: ticket T, wait for round T-1 (its MMAs have read the buffer and written their D)
-  // With fixed_order (EPDE_FLAG_DETERMINISTIC) rounds of one type are taken in a FIXED order (group 0 tile i, group 1 tile i, group 0 tile i+1, ...), so the
-  // order in which tile contributions are added to the accumulator images - and with it every bit of the
-  // gradient - does not depend on how the two groups happen to interleave.
-  auto acquire = [&](int r, uint32_t want) -> uint32_t {
-    if (sn == 0) {
-      uint32_t cur = want; int spin = 0;
-      if (fixed_order) do {
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(cur) : "r"(smem_u32(slot + 4 + r)) : "memory");
-        if (cur != want) { __nanosleep(32); if (++spin > (1 << 24)) __trap(); }
-      } while (cur != want);
-      slot[2 + g] = atomicAdd(slot + 1, 1u);
-    }
-    group_bar(g);
-    const uint32_t T = slot[2 + g];
+  // start of a round: the group's previous round has read the staging buffer and written its accumulator
+  bool pend = false;                                 // a round of this group is committed to rbar and not yet waited for
+  auto round_wait = [&]() {
     TC_ADD(0);
-    if (T > 0) mbar_wait(ring + ((T - 1) & 3), ((T - 1) >> 2) & 1);
+    if (pend) { mbar_wait(rbar, rph); rph ^= 1; pend = false; }
     fence_after();
     TC_ADD(5);
-    return T;
   };
-#define EPDE_P2_ROUND_ISSUE(T, RT, ISSUE)                                                                  \
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          \
-    fence_before(); group_bar(g); TC_ADD(1);                                                         \
-    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(ring + ((T) & 3)); } __syncwarp(); }          \
-    if (fixed_order && sn == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(smem_u32(slot + 4 + RT)), "r"(turn_next) : "memory"); \
-    TC_ADD(8);
+#define EPDE_P2_ROUND_ISSUE(ISSUE)                                                                       \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                         \
+    fence_before(); group_bar(g); TC_ADD(1);                                                             \
+    if (wq == 1) { if (elect_one()) { fence_after(); ISSUE; commit(rbar); } __syncwarp(); }              \
+    pend = true; TC_ADD(8);
 
 #define EPDE_P2_ISSUE(ISSUE)                                                                         \
     TC_ADD(0); fence_before(); group_bar(g); TC_ADD(1);                                              \
@@ -203,14 +254,12 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 
   const int64_t nt128 = (B + 127) / 128;
   const int64_t tstep = (int64_t)gridDim.x * P2G;
+  uint32_t lt = 0;                                   // tiles this group has started
 #pragma unroll 1
-  for (int64_t t = (int64_t)blockIdx.x * P2G + g; t < nt128; t += tstep) {
+  for (int64_t t = (int64_t)blockIdx.x * P2G + g; t < nt128; t += tstep, lt++) {
     const int64_t n = t * 128 + sn;
     const float* xcol = xt + (size_t)t * d_pad * 128 + sn;
-    // turn numbers of this tile's rounds: 2 * (local tile index) + group; group 0 skips the other group's turn when
-    // that group has no tile of the same index (only possible for the last one)
-    const uint32_t turn_want = 2u * (uint32_t)((t - ((int64_t)blockIdx.x * P2G + g)) / tstep) + (uint32_t)g;
-    const uint32_t turn_next = turn_want + ((g == 0 && t + 1 >= nt128) ? 2u : 1u);
+    const bool window_start = (lt % P2F) == 0;       // fresh accumulators; the previous window is flushed first
     const float wn = __ldg(wt + n);
     float ybar = -cm;
     if (n < B) {
@@ -236,8 +285,11 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       wait_st();
     }
     TC_ADD(4);
-    EPDE_P2_ISSUE(issue_matvec_rt(ks1, tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32),
-                                  kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32), idesc))
+    EPDE_P2_ISSUE(issue_matvec<KSC>(tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32),
+                                    kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32), idesc))
+    // the previous window's accumulators are flushed HERE: hardly anything is live in registers, the layer-1 MMAs run
+    // meanwhile, and the last round of the previous tile has had the whole x load to finish
+    if (window_start && lt > 0) { round_wait(); flush1(); flush2(); flush3(); TC_ADD(6); }
     EPDE_P2_WAIT()
     float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
     v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
@@ -304,22 +356,26 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       ze2[i] = (-2.f * a2[i]) * g2[i] * z[i];
       v[i] = ub2[i];
     }
+    publish_max(0, ub2);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(1))
+    float fn0;                                          // factor of this tile's g3 x ubar2 block (into fd[0] once the previous tile is flushed)
     {
-      const uint32_t T = acquire(0, turn_want);
-#pragma unroll
-      for (int i = 0; i < H; i++) {
-        stage_val(sM, i, g2[i]);
-        stage_val(sM, 20 + i, fmaf(-a3[i], a3[i], 1.f) * sw[L.w4() + i]);
-        stage_val(sM, 40 + i, ebar * g1[i]);
-        stage_val(sN, i, ub1[i]);
-        stage_val(sN, 20 + i, ub2[i]);
-        stage_val(sN, 40 + i, g1[i]);
+      round_wait();
+      {
+        float iub2;
+        const float s0 = scs[0], s1 = scs[1], s2 = scs[2] * ebar, s3 = scs[3], s4s = dyn_scale(0, iub2), s5 = scs[5];
+        fn0 = scs[26] * iub2;
+        stage_rows<8>(sM, [&](int r) -> float {
+          return r < 20 ? g2[r < 20 ? r : 0] * s0
+               : r < 40 ? (fmaf(-a3[(r >= 20 && r < 40) ? r - 20 : 0], a3[(r >= 20 && r < 40) ? r - 20 : 0], 1.f) * sw[L.w4() + ((r >= 20 && r < 40) ? r - 20 : 0)]) * s1
+               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] * s2 : 0.f; });
+        stage_rows<8>(sN, [&](int r) -> float {
+          return r < 20 ? ub1[r < 20 ? r : 0] * s3 : r < 40 ? ub2[(r >= 20 && r < 40) ? r - 20 : 0] * s4s
+               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] * s5 : 0.f; });
       }
       TC_ADD(7);
-      flush1(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, 0, issue_round<64>(tm + D1, sgb))
+      EPDE_P2_ROUND_ISSUE(issue_round<64>(tm + D1 + dlane, sgb, window_start ? 0u : 1u))
     }
     EPDE_P2_WAIT()
     // ---- S8: zbar3, s4 -> W3^T zbar3 -------------------------------------------------------------------
@@ -341,23 +397,25 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     float zb2[H];
 #pragma unroll
     for (int i = 0; i < H; i++) { zb2[i] = fmaf(fmaf(-a2[i], a2[i], 1.f), z[i], ze2[i]); v[i] = zb2[i]; }
+    publish_max(1, zb2); publish_max(2, zb3); publish_max(3, s4);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_P2_ISSUE(EPDE_P2_MV(2))
+    float fn1, fn2, fn3;
     {
-      const uint32_t T = acquire(1, turn_want);
-#pragma unroll
-      for (int i = 0; i < H; i++) {
-        stage_val(sM, i, zb2[i]);
-        stage_val(sM, 20 + i, zb3[i]);
-        stage_val(sM, 40 + i, s4[i]);
-        stage_val(sN, i, a1[i]);
-        stage_val(sN, 21 + i, a2[i]);
+      round_wait();
+      {
+        float i6, i7, i8;
+        const float s6 = dyn_scale(1, i6), s7 = dyn_scale(2, i7), s8 = dyn_scale(3, i8), s9 = scs[9], sa = scs[10];
+        fn1 = i6 * (1.f / 16384.f); fn2 = i7 * (1.f / 16384.f); fn3 = i8 * (1.f / 16384.f);
+        stage_rows<8>(sM, [&](int r) -> float {
+          return r < 20 ? zb2[r < 20 ? r : 0] * s6 : r < 40 ? zb3[(r >= 20 && r < 40) ? r - 20 : 0] * s7
+               : r < 60 ? s4[(r >= 40 && r < 60) ? r - 40 : 0] * s8 : r == 60 ? ybar * s9 : 0.f; });
+        stage_rows<6>(sN, [&](int r) -> float {          // a1 | 1 | a2 | 1, rows 42..47 zero
+          return r < 20 ? a1[r < 20 ? r : 0] * sa : r == 20 ? sa : r < 41 ? a2[(r >= 21 && r < 41) ? r - 21 : 0] * sa
+               : r == 41 ? sa : 0.f; });
       }
-      stage_val(sM, 60, ybar);                          // rows 61..63 / columns 42..47 hold stale finite values: ignored
-      stage_val(sN, 20, 1.f); stage_val(sN, 41, 1.f);
       TC_ADD(7);
-      flush2(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, 1, issue_round<48>(tm + D2, sgb))
+      EPDE_P2_ROUND_ISSUE(issue_round<48>(tm + D2 + dlane, sgb, window_start ? 0u : 1u))
     }
     EPDE_P2_WAIT()
     // ---- S10: zbar1;  round 3 ----------------------------------------------------------------------------
@@ -367,58 +425,53 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       float xv[64];
       load_x_cols(xv, xcol, 128, d, ks1);
       TC_ADD(9);
-      const uint32_t T = acquire(2, turn_want);
 #pragma unroll
-      for (int i = 0; i < H; i++) stage_val(sM, i, fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]));   // zbar1
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (c < ks1) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) stage_val(sN, 8 * c + i, xv[8 * c + i]);
-        }
+      for (int i = 0; i < H; i++) z[i] = fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]);      // zbar1
+      publish_max(4, z);
+      fence_before(); group_bar(g);
+      round_wait();
+      float fn4;
+      {
+        float i11;
+        const float s11 = dyn_scale(4, i11), s12 = scs[12];
+        fn4 = i11 * scs[27];
+        stage_rows<3>(sM, [&](int r) -> float { return r < 20 ? z[r < 20 ? r : 0] * s11 : 0.f; });   // rows 20..23 zero (24..63: stale finite values, ignored)
+        stage_rows<KSC>(sN, [&](int r) -> float { return xv[r < 64 ? r : 0] * s12; });      // x | 1 | 0...
       }
       TC_ADD(7);
-      flush3(); TC_ADD(6);
-      EPDE_P2_ROUND_ISSUE(T, 2, issue_round_rt(ks1, tm + D3, sgb))
+      EPDE_P2_ROUND_ISSUE(issue_round<K1>(tm + D3 + dlane, sgb, window_start ? 0u : 1u))
+      fd[4] = fn4;
     }
+    fd[0] = fn0; fd[1] = fn1; fd[2] = fn2; fd[3] = fn3;       // this tile's accumulators are flushed at the start of the next one
   }
 #undef EPDE_P2_ROUND_ISSUE
 #undef EPDE_P2_ISSUE
 #undef EPDE_P2_WAIT
 #undef EPDE_P2_MV
-  // ---- all rounds done: last flush, per-CTA gradient image -> global ----------------------------------------
+  // ---- all rounds issued: last flush of this group's accumulators ----------------------------------------------
+  if (lt > 0) { round_wait(); flush1(); flush2(); flush3(); }
   fence_before();
   __syncthreads();
   fence_after();
-  {
-    const uint32_t total = slot[1];
-    if (g == 0) {
-      if (total > 0) mbar_wait(ring + ((total - 1) & 3), ((total - 1) >> 2) & 1);
-      fence_after();
-      flush1(); flush2(); flush3();
-    }
-  }
-  fence_before();
-  __syncthreads();
-  {  // raw accumulator images -> GradLayout image of this CTA
-    const float* A1 = acc2; const float* A2 = acc2 + 64 * P2_S1; const float* A3 = A2 + 64 * P2_S2;
+  {  // the two group images -> GradLayout image of this CTA (fixed order: group 0 + group 1)
+    const float* I0 = imgs; const float* I1 = imgs + IMT;
     for (int e = tid; e < H * H; e += P2THREADS) {
       const int r = e / H, c = e % H;
-      acc[G.gW2() + e] = A1[r * P2_S1 + c] + A2[r * P2_S2 + c];
-      acc[G.gW3() + e] = A1[(20 + r) * P2_S1 + 20 + c] + A2[(20 + r) * P2_S2 + 21 + c];
-      acc[G.Gam() + e] = A1[(40 + r) * P2_S1 + 40 + c];
+      acc[G.gW2() + e] = I0[IM_W2 + r * IM_S + c] + I1[IM_W2 + r * IM_S + c];
+      acc[G.gW3() + e] = I0[IM_W3 + r * IM_S + c] + I1[IM_W3 + r * IM_S + c];
+      acc[G.Gam() + e] = I0[IM_G + r * IM_S + c] + I1[IM_G + r * IM_S + c];
     }
     for (int e = tid; e < H * d_pad; e += P2THREADS) {
       const int r = e / d_pad, c = e % d_pad;
-      acc[G.gW1() + e] = (c < d) ? A3[r * P2_S3 + c] : 0.f;
+      acc[G.gW1() + e] = (c < d) ? I0[IM_W1 + r * S3 + c] + I1[IM_W1 + r * S3 + c] : 0.f;
     }
     for (int r = tid; r < H; r += P2THREADS) {
-      acc[G.gb1() + r] = A3[r * P2_S3 + d];
-      acc[G.gb2() + r] = A2[r * P2_S2 + 20];
-      acc[G.gb3() + r] = A2[(20 + r) * P2_S2 + 41];
-      acc[G.gw4() + r] = A2[(40 + r) * P2_S2 + 20];
+      acc[G.gb1() + r] = I0[IM_W1 + r * S3 + d] + I1[IM_W1 + r * S3 + d];
+      acc[G.gb2() + r] = I0[IM_W2 + r * IM_S + 20] + I1[IM_W2 + r * IM_S + 20];
+      acc[G.gb3() + r] = I0[IM_W3 + r * IM_S + 20] + I1[IM_W3 + r * IM_S + 20];
+      acc[G.gw4() + r] = I0[IM_W4 + r] + I1[IM_W4 + r];
     }
-    if (tid == 0) acc[G.gb4()] = A2[60 * P2_S2 + 20];
+    if (tid == 0) acc[G.gb4()] = I0[IM_W4 + 20] + I1[IM_W4 + 20];
   }
   __syncthreads();
   float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;

@@ -10,7 +10,8 @@
  * Conventions
  *   - All pointers named d_* are DEVICE pointers (CUDA global memory); h_* are host pointers.
  *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); nothing in the
- *     library synchronises the host.  One in-flight call per workspace.
+ *     library synchronises the host.  One in-flight call per workspace; calls on different workspaces may run
+ *     concurrently from different threads (the library keeps no mutable global state).
  *   - Return value: 0 = ok; negative = EPDE_ERR_* (argument / unsupported configuration);
  *     positive = a cudaError_t reported by the runtime.  The library never aborts or throws.
  *   - The library allocates nothing persistent: the caller owns every buffer and queries the
@@ -34,7 +35,8 @@
 extern "C" {
 #endif
 
-#define EPDE_ABI_VERSION 2      /* 2: epde_desc.metric, epde_md_align */
+#define EPDE_ABI_VERSION 3      /* 2: epde_desc.metric, epde_md_align; 3: EPDE_FLAG_FFMA2 replaces epde_set_fused_impl,
+                                   device-side minibatch generator */
 #define EPDE_MAX_LAYERS 8   /* Linear layers per net */
 #define EPDE_MAX_K 8        /* eigenfunctions (nets) */
 
@@ -60,10 +62,15 @@ enum {
 };
 
 #define EPDE_FLAG_SORT 1u     /* sort_eigvals_in_training (src/pytorch_eigen_solver.py:217-221) */
-#define EPDE_FLAG_DETERMINISTIC 2u  /* bit-identical gradients run to run: the tensor-core kernels then add tile
-                                     contributions in a fixed order (costs ~7 % of the step); the FFMA2 kernels
-                                     always are; the generic path adds its fp64 partials with atomics (order-
-                                     dependent only at the 1e-16 level, invisible after the fp32 conversion) */
+#define EPDE_FLAG_DETERMINISTIC 2u  /* kept for ABI compatibility: both fused kernel families are bit-identical run to
+                                     run unconditionally (fixed accumulation order); the generic path adds its fp64
+                                     partials with atomics (order-dependent only at the 1e-16 level, invisible after
+                                     the fp32 conversion) */
+#define EPDE_FLAG_FFMA2 4u        /* kernel family of the fused path (reference architecture d -> 20 -> 20 -> 20 -> 1,
+                                     Tanh): set = FP32 FFMA2 kernels (sample-pair threads, weights broadcast from shared
+                                     memory); clear (default) = tcgen05 kernels (thread = TMEM lane = sample).  Both
+                                     compute the same quantities to the same tolerance.  Must be the same in the
+                                     epde_step_partial / epde_step_finish pair of a step. */
 
 typedef struct epde_desc {
   int32_t d;                            /* input dimension n_0 (data_set.tot_dim) */
@@ -177,15 +184,16 @@ int epde_adam_step(float* d_params, const float* d_grad, float* d_exp_avg, float
  *                            cvec is read from d_out_scalars on the device), d_avg is fp64 [param_count]
  *   epde_eig_stats_accumulate: d_stats[0..k) += eig, d_stats[k..2k) += eig^2   (:280-282)
  */
-/*
- * The three calls above in one launch with launch-invariant arguments (CUDA-graph replay of a whole training step):
- * d_state[0] = learning rate, d_state[1] = number of optimiser steps taken so far (fp64, incremented by the call).
- */
-int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_grad, float* d_m, float* d_v,
-                        double* d_state, double* d_avg, double* d_stats, const double* d_out_scalars, void* stream);
 int epde_average_accumulate(const epde_desc* desc, double* d_avg, const float* d_params,
                             const double* d_out_scalars, void* stream);
 int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const double* d_out_scalars, void* stream);
+/*
+ * epde_adam_step + epde_average_accumulate + epde_eig_stats_accumulate in ONE launch with launch-invariant arguments
+ * (CUDA-graph replay of a whole training step, :277-284): d_state[0] = learning rate, d_state[1] = number of optimiser
+ * steps taken so far (fp64, incremented by the call).
+ */
+int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_grad, float* d_m, float* d_v,
+                        double* d_state, double* d_avg, double* d_stats, const double* d_out_scalars, void* stream);
 
 /*
  * One-shot all-reduce (sum) of a small vector over NVLink peer memory, for the two exchanges of the sharded step
@@ -209,14 +217,6 @@ int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t 
  */
 int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* d_X, const double* ref_x,
                   const int32_t* ref_index, int32_t m, const float* d_diag, float* d_Xa, float* d_metric, void* stream);
-
-/*
- * Kernel family of the fused path (reference architecture d -> 20 -> 20 -> 20 -> 1, Tanh):
- *   0  FP32 FFMA2 kernels, sample-pair threads, weights broadcast from shared memory
- *   1  tcgen05 (kind::tf32, 3xTF32 split) kernels, thread = TMEM lane = sample
- * Both compute the same quantities to the same tolerance; the switch is process-wide.
- */
-int epde_set_fused_impl(int impl);
 
 #ifdef __cplusplus
 }

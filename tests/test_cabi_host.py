@@ -26,7 +26,7 @@ def test_exports_match_header(L):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.epde_abi_version() == 2
+    assert L.epde_abi_version() == _lib.ABI_VERSION == 3
     assert L.epde_error_string(0) == b"ok"
     assert b"workspace" in L.epde_error_string(-4)
 
@@ -131,12 +131,33 @@ def test_minibatch_edge_cases(L):
     assert L.epde_minibatch_indices(mt, C.byref(pos), 0, 4, out.ctypes.data_as(C.c_void_p)) == -6
 
 
-def test_fused_family_switch(L):
-    """epde_set_fused_impl: 0 = FFMA2 kernels, 1 = tcgen05 kernels (default); anything else is an argument error."""
-    assert L.epde_set_fused_impl(0) == 0
-    assert L.epde_set_fused_impl(1) == 0
-    assert L.epde_set_fused_impl(2) == -6
-    assert L.epde_set_fused_impl(-1) == -6
+def test_fused_family_is_a_descriptor_flag(L):
+    """The kernel family of the fused path travels in epde_desc.flags (EPDE_FLAG_FFMA2): the library has no process-wide
+    switch any more (ABI 3), and both settings describe a fused configuration with the same workspace layout."""
+    from eigenpde_nn_b200 import _lib
+    assert not hasattr(L, "epde_set_fused_impl")
+    sizes = []
+    for ffma2 in (False, True):
+        desc = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52, ffma2=ffma2)
+        assert bool(desc.flags & _lib.FLAG_FFMA2) == ffma2
+        assert L.epde_has_fused_path(C.byref(desc)) == 1
+        need = C.c_size_t()
+        assert L.epde_workspace_bytes(C.byref(desc), 4096, C.byref(need)) == 0
+        sizes.append(need.value)
+    assert sizes[0] == sizes[1]
+    big = _lib.make_desc([64, 20, 20, 20, 1], 3, "Tanh", 64)       # d + 1 > 64: outside the tensor-core family's x staging
+    assert L.epde_has_fused_path(C.byref(big)) == 0
+
+
+def test_activation_names_follow_the_reference(L):
+    """src/network_arch.py:27-32: a name torch.nn does not know falls back to CELU; a torch.nn activation without a
+    kernel here must raise instead of silently training CELU."""
+    from eigenpde_nn_b200 import _lib
+    assert _lib.activation_id("Tanh") == 0
+    assert _lib.activation_id("NoSuchActivation") == _lib.ACT_IDS["CELU"]
+    for name in ("GELU", "SiLU", "Softsign", "LeakyReLU"):
+        with pytest.raises(_lib.EpdeError):
+            _lib.activation_id(name)
 
 
 def test_argument_validation_of_the_newer_entry_points(L):

@@ -17,8 +17,7 @@ for (d, k, K, B) in cases:
     c = T._rand_case(d * 7 + k, d, k, [20, 20, 20], K, B)
     ref = T._oracle(c)
     for impl in (0, 1):
-        _lib.check(L.epde_set_fused_impl(impl), "impl")
-        eng = T._engine(c)
+        eng = T._engine(c, ffma2=(impl == 0))
         res = eng.step(c["idx"], T._flat(c["params"]), c["alpha"])
         grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), c["arch"], c["k"])
         try:
@@ -39,8 +38,7 @@ if "--time" in sys.argv:
     p = T._flat(c["params"])
     idx = torch.randint(0, K, (B,), device="cuda")
     for impl in (0, 1):
-        _lib.check(L.epde_set_fused_impl(impl), "impl")
-        eng = StepEngine(X, w, c["arch"], k, "Tanh", np.ones(d), 1.0, c["eig_w"])
+        eng = StepEngine(X, w, c["arch"], k, "Tanh", np.ones(d), 1.0, c["eig_w"], ffma2=(impl == 0))
         for _ in range(3): eng.step_device(idx, B, p, 20.0)
         torch.cuda.synchronize()
         ws = eng._workspace(B)

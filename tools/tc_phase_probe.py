@@ -10,7 +10,6 @@ d, k, B, Kd = 50, 3, 1 << 20, 1 << 22
 X = torch.zeros((Kd, 52), device="cuda"); X[:, :d] = 0.3 * torch.randn((Kd, d), device="cuda")
 w = torch.ones(Kd, device="cuda")
 L = _lib.lib()
-_lib.check(L.epde_set_fused_impl(1), "impl")
 eng = StepEngine(X, w, [d, 20, 20, 20, 1], k, "Tanh", np.ones(d), 1.0, [1.0, 0.8, 0.6])
 params = (0.5 * torch.randn(eng.n_params)).cuda()
 idx = torch.randint(0, Kd, (B,), device="cuda", dtype=torch.int64)
