@@ -61,6 +61,7 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 struct FusedWs {
   float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
   float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh)
+  float* stash;               // phase-1 intermediates of the tensor-core family (480 B per sample and net)
   size_t total;
 };
 FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
@@ -78,6 +79,7 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.part2 = (double*)take((size_t)kMaxCtas * 32 * 8);
   W.mx = (float*)take((size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4);
   W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
+  W.stash = (float*)take(tc::stash_floats(B, D->k) * 4);
   W.total = off;
   return W;
 }
@@ -142,7 +144,7 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   if (e != cudaSuccess) return (int)e;
   if (impl == 1)
     return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
-                       W.mx, W.nrm, st);
+                       W.mx, W.nrm, W.stash, st);
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
@@ -170,7 +172,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
                               impl == 1 ? W.mx : nullptr, impl == 1 ? W.nrm : nullptr);
   if (impl == 1) {
     int gx = 0;
-    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.pg, &gx, st);
+    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
     if (rc) return rc;
     const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
     k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);

@@ -10,15 +10,16 @@ struct Coef;
 namespace tc {
 
 size_t pack_floats(int d);          // floats of one net's packed weight image
+size_t stash_floats(int64_t B, int k);   // floats of the phase-1 -> phase-2 stash (epde_tc_fused.cuh)
 
 // phase 1: k_pack_tc + k_pass1_tc + k_sums_y + k_reduce_tc -> sums[1 + 2k + k(k+1)/2], ybuf[B][k]
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
-            cudaStream_t st);
+            float* stash, cudaStream_t st);
 
 // phase 2: k_pass2_tc -> per-CTA gradient images pg[(cta * k + net) * GradLayout.total()], *gx_out = CTAs per net
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
-           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st);
+           const float* ybuf, const Coef* coef, const float* stash, float* pg, int* gx_out, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace epde

@@ -16,10 +16,11 @@ namespace epde {
 namespace tc {
 
 size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
+size_t stash_floats(int64_t B, int k) { return (size_t)((B + 127) / 128) * (size_t)k * ST_TILE; }
 
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
-            cudaStream_t st) {
+            float* stash, cudaStream_t st) {
   const TcPack TL(d);
   k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
   const int64_t nt128 = (B + 127) / 128;
@@ -31,7 +32,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
   do {                                                                                                     \
     e = cudaFuncSetAttribute(k_pass1_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                   \
-    k_pass1_tc<__VA_ARGS__><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part, mx);      \
+    k_pass1_tc<__VA_ARGS__><<<dim3(gx, k), TTHREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, part, mx, stash); \
   } while (0)
   const bool std_pad = d_pad == (d + 3) / 4 * 4;
   if (std_pad && d == 50) EPDE_P1_LAUNCH(7, 50);          // the BASELINE shapes: exact d at compile time
@@ -58,7 +59,7 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 }
 
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
-           const float* ybuf, const Coef* coef, float* pg, int* gx_out, cudaStream_t st) {
+           const float* ybuf, const Coef* coef, const float* stash, float* pg, int* gx_out, cudaStream_t st) {
   const TcPack TL(d);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
@@ -70,7 +71,7 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   do {                                                                                                              \
     e = cudaFuncSetAttribute(k_pass2_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return (int)e;                                                                            \
-    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, pg);      \
+    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, stash, pg); \
   } while (0)
   const bool std_pad = d_pad == (d + 3) / 4 * 4;
   if (std_pad && d == 50) EPDE_P2_LAUNCH(7, 50);

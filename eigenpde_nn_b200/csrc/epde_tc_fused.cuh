@@ -310,11 +310,26 @@ __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, cons
 // k_pass1_tc: forward + Jacobian chain + energy for ONE net per CTA (blockIdx.y), 128-sample tiles
 //   part[(net * gridDim.x + blockIdx.x) * 2 + {0,1}] = sum w y, sum w e  (fp64);   ybuf[n][k]
 // ---------------------------------------------------------------------------------------------
+// Per-sample intermediates phase 1 hands to phase 2 (SURVEY H2 option C: stash instead of recompute):
+//   stash[tile128][net][vector][feature][128 samples], vectors 0 a1, 1 a2, 2 a3, 3 g2, 4 g1, 5 t = K g1   (fp32)
+// 480 B per sample and net, written and read exactly once with coalesced 128-byte rows (streaming: far larger than L2).
+constexpr int ST_VECS = 6;
+constexpr size_t ST_TILE = (size_t)ST_VECS * TH * 128;          // floats per tile and net
+__device__ __forceinline__ void stash_st(float* p, int vec, const float* v) {
+#pragma unroll
+  for (int i = 0; i < TH; i++) __stcs(p + (size_t)(vec * TH + i) * 128, v[i]);
+}
+__device__ __forceinline__ void stash_ld(const float* p, int vec, float (&v)[TH]) {
+#pragma unroll
+  for (int i = 0; i < TH; i++) v[i] = __ldcs(p + (size_t)(vec * TH + i) * 128);
+}
+
 // KSC = number of layer-1 k-steps (see k_pass2_tc)
 template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(TTHREADS, 1)
 k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
-           const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part, float* __restrict__ mx) {
+           const float* __restrict__ pwt, float* __restrict__ ybuf, double* __restrict__ part, float* __restrict__ mx,
+           float* __restrict__ stash) {
   constexpr int H = TH;
   const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
@@ -380,6 +395,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     const int64_t n = t * 128 + (tid & 127);
     const float wn = __ldg(wt + n);                                  // wt is padded to whole 256-sample tiles
     const bool more = t + tstep < nt128;
+    float* sp = stash + ((size_t)t * K + net) * ST_TILE + (tid & 127);
     TC_T0();
     // ---- x -> A (hi / lo), ones column at index d ----------------------------------------------
     {
@@ -413,12 +429,14 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
     for (int i = 0; i < H; i += 2) tanh_pair(z[i], z[i + 1], v[i], v[i + 1], t1[i], t1[i + 1]);
     v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
+    stash_st(sp, 0, v);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(0))
     // ---- a2 ---------------------------------------------------------------------------------
     tm_ld20(tl + dcol, z); TC_ADD(5);
 #pragma unroll
     for (int i = 0; i < H; i += 2) tanh_pair(z[i], z[i + 1], v[i], v[i + 1], t2[i], t2[i + 1]);
+    stash_st(sp, 1, v);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(1))
     // ---- a3, y, g3 --------------------------------------------------------------------------
@@ -430,6 +448,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       for (int i = 0; i < H; i += 2) {
         float a30, a31, t30, t31;
         tanh_pair(z[i], z[i + 1], a30, a31, t30, t31);
+        __stcs(sp + (size_t)(2 * TH + i) * 128, a30); __stcs(sp + (size_t)(2 * TH + i + 1) * 128, a31);
         const float2 w2 = make_float2(w4r[i], w4r[i + 1]);
         yy = ffma2(w2, make_float2(a30, a31), yy);
         const float2 g3 = fmul2(make_float2(t30, t31), w2);           // g3 = (1 - a3^2) w4
@@ -445,6 +464,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t2[i], t2[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g2
 #pragma unroll
     for (int i = 0; i < H; i += 2) mg2 = fmaxf(mg2, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+    stash_st(sp, 3, v);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(2))                                  // u1 = W2^T g2
     tm_ld20(tl + dcol, z); TC_ADD(5);
@@ -452,6 +472,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     for (int i = 0; i < H; i += 2) { const float2 q = fmul2(make_float2(t1[i], t1[i + 1]), make_float2(z[i], z[i + 1])); v[i] = q.x; v[i + 1] = q.y; }   // g1
 #pragma unroll
     for (int i = 0; i < H; i += 2) mg1 = fmaxf(mg1, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+    stash_st(sp, 4, v);
     store_vec24(tl + ahi, tl + alo, v);
     EPDE_TC_STAGE(EPDE_TC_MV(4))                                  // K g1
     tm_ld20(tl + dcol, z); TC_ADD(5);
@@ -459,6 +480,7 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
     for (int i = 0; i < H; i += 2) { e0 = fmaf(v[i], z[i], e0); e1 = fmaf(v[i + 1], z[i + 1], e1); mt = fmaxf(mt, fmaxf(fabsf(z[i]), fabsf(z[i + 1]))); }
     const float e = e0 + e1;
+    stash_st(sp, 5, z);
     my = fmaxf(my, fabsf(y));
 #undef EPDE_TC_STAGE
 #undef EPDE_TC_MV

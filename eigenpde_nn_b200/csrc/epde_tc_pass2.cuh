@@ -50,19 +50,20 @@ __host__ __device__ constexpr int im_total(int K1) { return IM_W1 + 20 * im_s3(K
 __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
-// Stage NCH chunks of 8 features of this thread's sample: get(r) returns the SCALED value of feature row r (r is a
-// compile-time constant after unrolling, so the selection inside `get` costs nothing).  v = hi + lo with fp16 hi, lo.
-template <int NCH, typename F>
-__device__ __forceinline__ void stage_rows(uint32_t img_hi, F get) {
+// Stage NCH chunks of 8 features of this thread's sample: get(r) returns the value of feature row r, sc(r) its power-of-
+// two scale (r is a compile-time constant after unrolling, so the selections inside cost nothing; rows 2j, 2j + 1 always
+// belong to the same vector).  v * s = hi + lo with fp16 hi, lo; packed f32x2 arithmetic: 6 instructions per pair.
+template <int NCH, typename F, typename S>
+__device__ __forceinline__ void stage_rows(uint32_t img_hi, F get, S sc) {
 #pragma unroll
   for (int c = 0; c < NCH; c++) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float x0 = get(8 * c + 2 * j), x1 = get(8 * c + 2 * j + 1);
-      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(x1), "f"(x0));       // x0 -> low half
-      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+      const float2 x = fmul2(make_float2(get(8 * c + 2 * j), get(8 * c + 2 * j + 1)), splat(sc(8 * c + 2 * j)));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(x.y), "f"(x.x));       // x.x -> low half
+      const float2 r = ffma2(splat(-1.f), __half22float2(*reinterpret_cast<const __half2*>(&h[j])), x);   // exact residual
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(r.y), "f"(r.x));
     }
     sts128(img_hi + (uint32_t)c * SG_SMN, h); sts128(img_hi + SG_IMG + (uint32_t)c * SG_SMN, l);
   }
@@ -104,7 +105,7 @@ template <int KSC, int DC = 0>
 __global__ void __launch_bounds__(P2THREADS, 1)
 k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d_rt, int d_pad_rt, int K,
            const float* __restrict__ pwt, const float* __restrict__ ybuf, const Coef* __restrict__ coef,
-           float* __restrict__ pg) {
+           const float* __restrict__ stash, float* __restrict__ pg) {
   constexpr int H = TH;
   const int d = DC > 0 ? DC : d_rt;                  // DC > 0: the exact input dimension is a compile-time constant as well
   const int d_pad = DC > 0 ? (DC + 3) / 4 * 4 : d_pad_rt;
@@ -269,69 +270,23 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     ybar *= wn;                                     // ybar_n = w_n (sum_j Cw[j] y_{n,j} - cm)
     const float ebar = wn * ecoef;
     TC_T0();
-    // ---- S0: x -> A -------------------------------------------------------------------------------
-    {
-      float xv[64];
-      load_x_cols(xv, xcol, 128, d, ks1);
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (c < ks1) {
-          float hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) split_tf32(xv[8 * c + i], hi[i], lo[i]);
-          tm_st8(tl + ahi + 8 * c, hi); tm_st8(tl + alo + 8 * c, lo);
-        }
-      }
-      wait_st();
-    }
-    TC_ADD(4);
-    EPDE_P2_ISSUE(issue_matvec<KSC>(tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.W1f(0) * 4, 128, K1 * 32),
-                                    kdesc(sbase + L.W1f(1) * 4, 128, K1 * 32), idesc))
-    // the previous window's accumulators are flushed HERE: hardly anything is live in registers, the layer-1 MMAs run
-    // meanwhile, and the last round of the previous tile has had the whole x load to finish
-    if (window_start && lt > 0) { round_wait(); flush1(); flush2(); flush3(); TC_ADD(6); }
-    EPDE_P2_WAIT()
+    // ---- phase 1's per-sample intermediates come back from the stash (no forward / Jacobian recompute) ----------
+    // t, a1, g1 (needed first) are requested before the previous tile's accumulators are flushed, the rest after it:
+    // the flush hides the DRAM latency of the first half and bounds the registers in flight.
+    const float* sp = stash + ((size_t)t * K + net) * ST_TILE + sn;
     float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
-    v[20] = 1.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;
-    // ---- S1 .. S2: a1, a2 ---------------------------------------------------------------------------
-    tm_ld20(tl + dcol, z);
+    stash_ld(sp, 5, z); stash_ld(sp, 0, a1); stash_ld(sp, 4, g1);
+    if (t + tstep < nt128) {      // the next tile's stash rows (120 rows of 512 B) towards L2: 480 lines, 4 per thread
+      const char* nx = reinterpret_cast<const char*>(stash + ((size_t)(t + tstep) * K + net) * ST_TILE);
 #pragma unroll
-    for (int i = 0; i < H; i++) { a1[i] = tanh1(z[i]); v[i] = a1[i]; }
-    tm_st16(pkA, a1); tm_st4(pkA + 16, a1 + 16);        // a1 is parked in TMEM until S5
-    store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(0))
-    EPDE_P2_WAIT()
-    tm_ld20(tl + dcol, z);
-#pragma unroll
-    for (int i = 0; i < H; i++) { a2[i] = tanh1(z[i]); v[i] = a2[i]; }
-    store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(1))
-    EPDE_P2_WAIT()
-    // ---- S3: a3, g3 -> u2 ---------------------------------------------------------------------------
-    tm_ld20(tl + dcol, z);
-    v[20] = 0.f;                                      // no bias row from here on
-#pragma unroll
-    for (int i = 0; i < H; i++) { a3[i] = tanh1(z[i]); v[i] = fmaf(-a3[i], a3[i], 1.f) * sw[L.w4() + i]; }   // g3
-    store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(3))
-    EPDE_P2_WAIT()
-    // ---- S4: g2 -> u1 -------------------------------------------------------------------------------
-    tm_ld20(tl + dcol, z);
-#pragma unroll
-    for (int i = 0; i < H; i++) { g2[i] = fmaf(-a2[i], a2[i], 1.f) * z[i]; v[i] = g2[i]; }
-    store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(2))
-    EPDE_P2_WAIT()
-    // ---- S5: g1 -> K g1 -----------------------------------------------------------------------------
-    tm_ld16(pkA, a1); tm_ld4(pkA + 16, a1 + 16);
-    tm_ld20(tl + dcol, z);
-#pragma unroll
-    for (int i = 0; i < H; i++) { g1[i] = fmaf(-a1[i], a1[i], 1.f) * z[i]; v[i] = g1[i]; }
-    store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(4))
-    EPDE_P2_WAIT()
+      for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)(q * 128 + sn) << 7)));
+    }
+    if (window_start && lt > 0) { round_wait(); flush1(); flush2(); flush3(); TC_ADD(6); }
+    stash_ld(sp, 1, a2); stash_ld(sp, 3, g2); stash_ld(sp, 2, a3);
+    v[20] = 0.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;       // no bias rows in the reverse sweeps
+    tm_st16(pkA, a1); tm_st4(pkA + 16, a1 + 16);              // a1 is parked in TMEM until S9 / S10
+    TC_ADD(4);
     // ---- S6: gbar1 = 2 ebar K g1, ubar1 -> gbar2 = W2 ubar1 --------------------------------------------
-    tm_ld20(tl + dcol, z);
     float ub1[H];
     {
       const float e2 = 2.f * ebar;
@@ -367,12 +322,14 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
         const float s0 = scs[0], s1 = scs[1], s2 = scs[2] * ebar, s3 = scs[3], s4s = dyn_scale(0, iub2), s5 = scs[5];
         fn0 = scs[26] * iub2;
         stage_rows<8>(sM, [&](int r) -> float {
-          return r < 20 ? g2[r < 20 ? r : 0] * s0
-               : r < 40 ? (fmaf(-a3[(r >= 20 && r < 40) ? r - 20 : 0], a3[(r >= 20 && r < 40) ? r - 20 : 0], 1.f) * sw[L.w4() + ((r >= 20 && r < 40) ? r - 20 : 0)]) * s1
-               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] * s2 : 0.f; });
+          return r < 20 ? g2[r < 20 ? r : 0]
+               : r < 40 ? fmaf(-a3[(r >= 20 && r < 40) ? r - 20 : 0], a3[(r >= 20 && r < 40) ? r - 20 : 0], 1.f) * sw[L.w4() + ((r >= 20 && r < 40) ? r - 20 : 0)]
+               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
+          [&](int r) -> float { return r < 20 ? s0 : r < 40 ? s1 : s2; });
         stage_rows<8>(sN, [&](int r) -> float {
-          return r < 20 ? ub1[r < 20 ? r : 0] * s3 : r < 40 ? ub2[(r >= 20 && r < 40) ? r - 20 : 0] * s4s
-               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] * s5 : 0.f; });
+          return r < 20 ? ub1[r < 20 ? r : 0] : r < 40 ? ub2[(r >= 20 && r < 40) ? r - 20 : 0]
+               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
+          [&](int r) -> float { return r < 20 ? s3 : r < 40 ? s4s : s5; });
       }
       TC_ADD(7);
       EPDE_P2_ROUND_ISSUE(issue_round<64>(tm + D1 + dlane, sgb, window_start ? 0u : 1u))
@@ -408,11 +365,13 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
         const float s6 = dyn_scale(1, i6), s7 = dyn_scale(2, i7), s8 = dyn_scale(3, i8), s9 = scs[9], sa = scs[10];
         fn1 = i6 * (1.f / 16384.f); fn2 = i7 * (1.f / 16384.f); fn3 = i8 * (1.f / 16384.f);
         stage_rows<8>(sM, [&](int r) -> float {
-          return r < 20 ? zb2[r < 20 ? r : 0] * s6 : r < 40 ? zb3[(r >= 20 && r < 40) ? r - 20 : 0] * s7
-               : r < 60 ? s4[(r >= 40 && r < 60) ? r - 40 : 0] * s8 : r == 60 ? ybar * s9 : 0.f; });
+          return r < 20 ? zb2[r < 20 ? r : 0] : r < 40 ? zb3[(r >= 20 && r < 40) ? r - 20 : 0]
+               : r < 60 ? s4[(r >= 40 && r < 60) ? r - 40 : 0] : r == 60 ? ybar : 0.f; },
+          [&](int r) -> float { return r < 20 ? s6 : r < 40 ? s7 : r < 60 ? s8 : s9; });
         stage_rows<6>(sN, [&](int r) -> float {          // a1 | 1 | a2 | 1, rows 42..47 zero
-          return r < 20 ? a1[r < 20 ? r : 0] * sa : r == 20 ? sa : r < 41 ? a2[(r >= 21 && r < 41) ? r - 21 : 0] * sa
-               : r == 41 ? sa : 0.f; });
+          return r < 20 ? a1[r < 20 ? r : 0] : r == 20 ? 1.f : r < 41 ? a2[(r >= 21 && r < 41) ? r - 21 : 0]
+               : r == 41 ? 1.f : 0.f; },
+          [&](int) -> float { return sa; });
       }
       TC_ADD(7);
       EPDE_P2_ROUND_ISSUE(issue_round<48>(tm + D2 + dlane, sgb, window_start ? 0u : 1u))
@@ -435,8 +394,9 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
         float i11;
         const float s11 = dyn_scale(4, i11), s12 = scs[12];
         fn4 = i11 * scs[27];
-        stage_rows<3>(sM, [&](int r) -> float { return r < 20 ? z[r < 20 ? r : 0] * s11 : 0.f; });   // rows 20..23 zero (24..63: stale finite values, ignored)
-        stage_rows<KSC>(sN, [&](int r) -> float { return xv[r < 64 ? r : 0] * s12; });      // x | 1 | 0...
+        stage_rows<3>(sM, [&](int r) -> float { return r < 20 ? z[r < 20 ? r : 0] : 0.f; },   // rows 20..23 zero (24..63: stale finite values, ignored)
+                      [&](int) -> float { return s11; });
+        stage_rows<KSC>(sN, [&](int r) -> float { return xv[r < 64 ? r : 0]; }, [&](int) -> float { return s12; });      // x | 1 | 0...
       }
       TC_ADD(7);
       EPDE_P2_ROUND_ISSUE(issue_round<K1>(tm + D3 + dlane, sgb, window_start ? 0u : 1u))
