@@ -10,8 +10,11 @@ One step = one pass of the hot path (src/pytorch_eigen_solver.py:212-233) over o
 B = 2^20 samples per GPU (weak scaling: the global batch is N * 2^20, sharded by contiguous slices).
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with the index batch already on the device;
-`e2e` = the same step through the host-facing API with host (pinned) index/parameter buffers and
-the gradient + scalars read back every step.
+`e2e` = the same step through the host-facing API: every step draws a FRESH minibatch from the reference's
+MT19937 stream on the device (bit-exact with random.choices, src/data_set.py:67; generation inside the timed
+region, one step ahead on a second stream), uploads the parameters from pinned host memory and reads the
+gradient + scalars back.  With N > 1 a pre-timing self-check compares the N-rank step with a single-rank
+step on the union batch (`parity`).  `extra` (N = 1 only) carries BASELINE configs 4 and 5.
 """
 from __future__ import annotations
 
@@ -164,6 +167,55 @@ def cpu_port_rate(B, steps, warmup, seed=0):
     return B / statistics.median(t_full), B / statistics.median(t_lg), torch.get_num_threads()
 
 
+def extra_workloads(dev, X, w):
+    """BASELINE configs 4 and 5 as driver-visible numbers (N = 1): one rank's shard of config 4 (50-D, k = 6, 2^21 of the
+    2^24 samples per step) and config 5 (wide MLP 4 x 256, 50-D, k = 4, per-layer tcgen05 GEMMs of the generic family)."""
+    import numpy as np
+    import torch
+    from eigenpde_nn_b200.engine import StepEngine
+    out = {}
+
+    def timed(eng, B, steps, warm=3):
+        g = torch.Generator(device=dev).manual_seed(5)
+        idx = [torch.randint(0, K_DATA, (B,), generator=g, device=dev, dtype=torch.int64) for _ in range(2)]
+        params = (0.5 * torch.randn(eng.n_params, generator=torch.Generator().manual_seed(9))).to(dev)
+        for i in range(warm):
+            eng.step_device(idx[i & 1], B, params, ALPHA)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            eng.step_device(idx[i & 1], B, params, ALPHA)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, float(eng.out[0])
+
+    B4 = 1 << 21
+    eng = StepEngine(X, w, ARCH, 6, "Tanh", np.ones(D), BETA, [1.0, 0.8, 0.6, 0.3, 0.2, 0.1], device=dev)
+    ms, loss = timed(eng, B4, 10)
+    flop4 = 2 * 6 * (6 * M_MACS - 50 * 20)
+    out["cfg4_50d_k6_shard"] = {"workload": "50-D, k=6, one rank's 2^21-sample shard of the 2^24-sample step", "batch": B4,
+                                "samples_per_s": B4 / (ms * 1e-3), "ms_per_step": ms, "flop_per_sample": flop4,
+                                "frac_fp32_ffma": flop4 * B4 / (ms * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS, "fused": bool(eng.fused),
+                                "loss": loss}
+    del eng
+    torch.cuda.empty_cache()
+    Bw = 1 << 18
+    archw = [50, 256, 256, 256, 256, 1]
+    eng = StepEngine(X, w, archw, 4, "Tanh", np.ones(D), BETA, [1.0, 0.8, 0.6, 0.3], device=dev)
+    ms, loss = timed(eng, Bw, 4, warm=2)
+    Mw = sum(archw[l] * archw[l + 1] for l in range(len(archw) - 1))
+    flopw = 2 * 4 * (6 * Mw - archw[0] * archw[1])
+    out["cfg5_wide_4x256_k4"] = {"workload": "50-D, 4x256 Tanh, k=4 (per-layer tcgen05 3xTF32 GEMMs)", "batch": Bw,
+                                 "samples_per_s": Bw / (ms * 1e-3), "ms_per_step": ms, "flop_per_sample": flopw,
+                                 "achieved_tflops": flopw * Bw / (ms * 1e-3) / 1e12,
+                                 "frac_tf32x3_ceiling": flopw * Bw / (ms * 1e-3) / 1e12 / (TENSOR_PEAK_TFLOPS / 6.0),
+                                 "fused": bool(eng.fused), "loss": loss}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path, timed on the host cores.
     /root/reference is Python and cannot travel to the GPU box; the oracle port restates it op by op
@@ -194,6 +246,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-4 / config-5 side measurements (N = 1)")
     ap.add_argument("--knets", type=int, default=3, help="k (default 3 = the headline workload; 6 with --batch 2097152 on "
                                                          "8 GPUs = BASELINE config 4, an ad-hoc run, not the bench line)")
     args = ap.parse_args()
@@ -230,16 +283,42 @@ def main():
     assert eng.fused
     params_h = init_params(7).pin_memory()
     params = params_h.to(dev)
-    nbatch = 4                                              # distinct index batches, cycled
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    idx_dev = [torch.randint(0, K_DATA, (B,), generator=g, device=dev, dtype=torch.int64) for _ in range(nbatch)]
-    idx_pin = [t.cpu().pin_memory() for t in idx_dev]
+    # minibatch indices: the reference's own stream (MT19937, random.seed on every rank -> the same GLOBAL stream), drawn
+    # on the device; rank r keeps the r-th contiguous slice of each global batch
+    import random
+    from eigenpde_nn_b200.engine import DeviceMinibatch, DrawAhead
+    random.seed(20251020)
+    mb = DeviceMinibatch(K_DATA, dev).seed_from_python()
+    nbatch = 4                                              # distinct index batches for the device-resident timing, cycled
+    idx_dev = [mb.draw(world * B, lo=rank * B, n=B) for _ in range(nbatch)]
 
     def barrier():
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+
+    exchange = "none" if world == 1 else ("peer" if eng._exchange is not None else "nccl")
+    # ---- N > 1: the sharded step against a single-rank step on the union batch (same kernels, no exchange) -----------
+    parity = None
+    if world > 1:
+        idx_union = mb.draw(world * B)                      # every rank holds the whole global batch of this draw
+        o_n, g_n = eng.step_device(idx_union[rank * B:(rank + 1) * B].contiguous(), B, params, ALPHA)
+        o_n, g_n = o_n.clone(), g_n.clone()
+        single = StepEngine(X, w, ARCH, KNETS, "Tanh", np.ones(D), BETA, EIG_W, device=dev)
+        o_1, g_1 = single.step_device(idx_union, world * B, params, ALPHA)
+        torch.cuda.synchronize()
+        rel_out = float(((o_n[:4 + KNETS] - o_1[:4 + KNETS]).abs() / o_1[:4 + KNETS].abs().clamp_min(1e-300)).max())
+        rel_grad = float((g_n - g_1).norm() / g_1.norm())
+        same_cvec = bool(torch.equal(o_n[4 + KNETS:4 + 2 * KNETS], o_1[4 + KNETS:4 + 2 * KNETS]))
+        t = torch.tensor([rel_out, rel_grad, 0.0 if same_cvec else 1.0], dtype=torch.float64, device=dev)
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = {"n_rank_vs_single_rank": {"scalars_max_rel": float(t[0]), "grad_norm_rel": float(t[1]),
+                                            "cvec_equal": bool(t[2] == 0.0)},
+                  "tolerance": 1e-5, "ok": bool(t[0] <= 1e-5 and t[1] <= 1e-5 and t[2] == 0.0), "exchange": exchange}
+        del single, idx_union
+        torch.cuda.empty_cache()
 
     # ---- device-resident timing ------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -285,16 +364,13 @@ def main():
     out_pin = torch.empty(eng.out.numel(), dtype=torch.float64).pin_memory()
     grad_pin = torch.empty(eng.n_params, dtype=torch.float32).pin_memory()
     par_stage = torch.empty_like(params)
-    from eigenpde_nn_b200.engine import MinibatchPipeline
-    pipe = MinibatchPipeline(B, dev)                                   # H2D of step i+1's indices runs behind step i
-    pipe.prefetch(idx_pin[0])
+    ahead = DrawAhead(mb, world * B, lo=rank * B, n=B).start()          # step i+1's indices are generated behind step i
 
     def e2e_step(i):
-        idx_stage = pipe.acquire()                                     # H2D (copy stream): this step's minibatch indices
+        idx_stage = ahead.take()                                       # fresh draw from the MT19937 stream (device, side stream)
         par_stage.copy_(params_h, non_blocking=True)                   # H2D: current parameters
         o, gr = eng.step_device(idx_stage, B, par_stage, ALPHA)
-        pipe.release()
-        pipe.prefetch(idx_pin[(i + 1) % nbatch])                       # next step's indices, every step, 8 B per sample
+        ahead.done_with(idx_stage)
         out_pin.copy_(o, non_blocking=True)                            # D2H: loss / eigenvalues / penalty
         grad_pin.copy_(gr, non_blocking=True)                          # D2H: gradient for the host optimiser
         torch.cuda.current_stream().synchronize()                      # update_step returns host values (:236)
@@ -333,15 +409,17 @@ def main():
         pj = json.load(open(prof))
         traffic = pj.get("dram_bytes_per_launch") if pj.get("batch") == B else None
     line = {
-        "metric": "samples/s, fused loss+grad step, 50-D k=3", "value": value, "unit": "samples/s",
+        "metric": "samples/s, fused loss+grad step, 50-D k=%d" % KNETS, "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ex1_50d_k%d" % KNETS, "d": D, "k": KNETS, "arch": ARCH, "activation": "Tanh",
                    "batch_per_gpu": B, "global_batch": world * B, "dataset_rows": K_DATA,
-                   "parallelism": "dp%d (batch sharded, 2 NCCL allreduces/step)" % world if world > 1 else "single GPU",
+                   "parallelism": ("dp%d (batch sharded by contiguous slices; 2 small all-reduces per step: %s)" % (
+                       world, "one-shot NVLink peer-memory kernel epde_peer_allreduce" if exchange == "peer" else "NCCL"))
+                   if world > 1 else "single GPU", "exchange": exchange,
                    "l2": "inputs larger than L2: 872 MB data set gathered by fresh random indices each step"},
         "loss": float(out_h[0]), "eig_vals": [float(v) for v in out_h[4:4 + KNETS]],
-        # dominant kernel: k_pass2_tc (tcgen05 kind::tf32, 3xTF32 split).  `peak` is the driver-measured dense bf16
+        # dominant kernel: k_pass2_tc (tcgen05: kind::tf32 3xTF32 mat-vecs, kind::f16 two-term-split gradient rounds).  `peak` is the driver-measured dense bf16
         # figure (sustained: the kernel is timed inside a long step); a TF32 operand pair runs at half that rate and
         # the fp32-accurate split needs three MMAs per product, so 1/6 of `peak` is the ceiling of this formulation
         # before any padding (N 20 -> 32, stacked gradient rounds).  `fp32_ffma` keeps the FP32-pipe comparison of the
@@ -358,10 +436,18 @@ def main():
                               "frac_fp32_ffma": FLOP_ALG * B / ((t_p1 + t_p2) * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS,
                               "ms_phase1": t_p1, "ms_phase2": t_p2, "flop_per_sample": FLOP_ALG},
                      "hbm": {"achieved_gbs": BYTES_ALG * B / ((t_p1 + t_p2) * 1e-3) / 1e9, "peak_gbs": 6544.3}},
-        "e2e": {"value": total / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 8 * B + 4 * eng.n_params,
-                "d2h_bytes_per_step": 8 * eng.out.numel() + 4 * eng.n_params},
-        "gpu_launches": 8 * args.steps, "clocks": clocks,
+        "e2e": {"value": total / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 4 * eng.n_params,
+                "d2h_bytes_per_step": 8 * eng.out.numel() + 4 * eng.n_params,
+                "minibatch": "fresh draw every step from the reference's MT19937 stream, generated on the device inside the "
+                             "timed region (epde_minibatch_indices_device, %d draws per rank and step: every rank advances the "
+                             "global stream), one step ahead on a second stream; no index upload" % (world * B)},
+        # per step: memset, k_gather128, k_pack_tc, k_pass1_tc, k_sums_y, k_reduce_tc, k_coef, k_pass2_tc, k_fin2 (+ 2 exchange kernels)
+        "gpu_launches": (8 + (2 if world > 1 else 0)) * args.steps, "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if world == 1 and not args.no_extra and KNETS == 3:
+        line["extra"] = extra_workloads(dev, X, w)
     if world == 1 and not args.no_cpu_baseline:
         full, lg, cores = cpu_port_rate(20000, 12, 3)
         line["cpu_baseline"] = {"value": lg, "unit": "samples/s", "cores": cores, "kind": "port",

@@ -22,7 +22,7 @@ ABI_VERSION = 3
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
-           "epde_minibatch_indices", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
+           "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
            "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_peer_allreduce"]
 
 
@@ -59,6 +59,7 @@ def lib():
         L.epde_step.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp, vp]
         L.epde_forward.argtypes = [dp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
         L.epde_minibatch_indices.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, vp]
+        L.epde_minibatch_indices_device.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
         L.epde_mt_seed.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_int32)]
         L.epde_adam_step.argtypes = [vp, vp, vp, vp, i64, f64, i64, vp]
         L.epde_average_accumulate.argtypes = [dp, vp, vp, vp, vp]

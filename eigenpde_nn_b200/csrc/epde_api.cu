@@ -11,6 +11,7 @@
 #include "epde_generic.cuh"
 #include "epde_tc_api.h"
 #include "epde_md_align.cuh"
+#include "epde_mt.cuh"
 
 using namespace epde;
 
@@ -362,18 +363,17 @@ int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t
 }
 
 // ---- host-side MT19937 (CPython `random` compatible) ----------------------------------------
-static void mt_twist(uint32_t* mt) {
+static void mt_twist(uint32_t* mt) {        // three index ranges instead of two modulo operations per word
   const int N = 624, M = 397;
-  for (int kk = 0; kk < N; kk++) {
-    const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % N] & 0x7fffffffu);
-    mt[kk] = mt[(kk + M) % N] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-  }
+  auto f = [](uint32_t a, uint32_t b) { const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu); return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); };
+  int kk = 0;
+  for (; kk < N - M; kk++) mt[kk] = mt[kk + M] ^ f(mt[kk], mt[kk + 1]);
+  for (; kk < N - 1; kk++) mt[kk] = mt[kk + (M - N)] ^ f(mt[kk], mt[kk + 1]);
+  mt[N - 1] = mt[M - 1] ^ f(mt[N - 1], mt[0]);
 }
 static inline uint32_t mt_next(uint32_t* mt, int32_t* pos) {
   if (*pos >= 624) { mt_twist(mt); *pos = 0; }
-  uint32_t y = mt[(*pos)++];
-  y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-  return y;
+  return mt_temper(mt[(*pos)++]);
 }
 
 int epde_minibatch_indices(uint32_t* mt, int32_t* pos, int64_t K, int64_t B, int64_t* out) {
@@ -388,6 +388,17 @@ int epde_minibatch_indices(uint32_t* mt, int32_t* pos, int64_t K, int64_t B, int
     out[i] = j;
   }
   return EPDE_OK;
+}
+
+int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total, int64_t out_lo, int64_t out_n,
+                                  uint32_t* d_raw, int64_t* d_idx, void* stream) {
+  if (!d_state || !d_raw || (!d_idx && out_n > 0)) return EPDE_ERR_NULL;
+  if (K < 1 || B_total < 0 || out_lo < 0 || out_n < 0 || out_lo + out_n > B_total) return EPDE_ERR_ARG;
+  if (((uintptr_t)d_raw & 7) || ((uintptr_t)d_state & 3)) return EPDE_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, 2 * B_total, d_raw);
+  if (out_n > 0) k_mt_to_idx<<<(unsigned)((out_n + 255) / 256), 256, 0, st>>>(d_raw, K, out_lo, out_n, d_idx);
+  return (int)cudaGetLastError();
 }
 
 int epde_mt_seed(const uint32_t* key, int32_t key_len, uint32_t* mt, int32_t* pos) {

@@ -187,6 +187,103 @@ class EigenLossFn(torch.autograd.Function):
         return (None, None, None) + tuple(outs)
 
 
+class DeviceMinibatch:
+    """The reference's minibatch index stream (src/data_set.py:31,67: `random.choices(range(K), cum_weights=1..K, k=B)`)
+    continued ON THE DEVICE: the MT19937 state of Python's `random` is uploaded once (`seed_from_python`), every `draw`
+    is two kernels of the library (`epde_minibatch_indices_device`) with no host involvement, and `sync_to_python` hands
+    the advanced state back to `random.setstate` -- after it, `random` is exactly where the reference would have left it.
+    With world > 1 every rank advances the whole global stream and keeps its own contiguous slice."""
+
+    def __init__(self, K, device, lib=None):
+        self.lib = lib if lib is not None else _lib.lib()
+        self.K = int(K)
+        self.device = torch.device(device)
+        self.state = torch.zeros(625, dtype=torch.int32, device=self.device)      # 624 words + position (uint32 bit patterns)
+        self._raw = None
+        self._py_meta = None
+        self.seeded = False
+
+    def seed_from_python(self):
+        import random
+        version, st, gauss = random.getstate()
+        self._py_meta = (version, gauss)
+        host = np.array(st, dtype=np.uint32).view(np.int32)
+        self.state.copy_(torch.from_numpy(host))
+        self.seeded = True
+        return self
+
+    def sync_to_python(self):
+        """Download the generator state and install it in Python's `random` (synchronises the device)."""
+        import random
+        assert self.seeded
+        st = self.state.cpu().numpy().view(np.uint32)
+        version, gauss = self._py_meta
+        random.setstate((version, tuple(int(v) for v in st), gauss))
+
+    def draw(self, B_total, out=None, lo=0, n=None):
+        """Enqueue B_total draws on the current stream; the indices of draws [lo, lo + n) go to `out` (int64, device)."""
+        assert self.seeded, "call seed_from_python() first"
+        n = B_total - lo if n is None else n
+        if out is None:
+            out = torch.empty(n, dtype=torch.int64, device=self.device)
+        if B_total == 0:
+            return out
+        if self._raw is None or self._raw.numel() < 2 * B_total:
+            self._raw = torch.empty(2 * B_total, dtype=torch.int32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.epde_minibatch_indices_device(_ptr(self.state), C.c_int64(self.K), C.c_int64(B_total),
+                                                          C.c_int64(lo), C.c_int64(n), _ptr(self._raw), _ptr(out), st),
+                   "epde_minibatch_indices_device")
+        return out
+
+
+class DrawAhead:
+    """Draws the next step's minibatch on a second stream while the current step computes (the index stream does not
+    depend on the step's result; the generator is a single CTA and the step's kernels leave an SM idle).
+        ahead = DrawAhead(mb, B_total, lo, n); ahead.start()
+        for ...: idx = ahead.take(); <enqueue the step reading idx>; ahead.done_with(idx) ..."""
+
+    def __init__(self, mb: DeviceMinibatch, B_total, lo=0, n=None):
+        self.mb, self.B_total, self.lo = mb, B_total, lo
+        self.n = B_total - lo if n is None else n
+        dev = mb.device
+        self.buf = [torch.empty(self.n, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(dev))
+        self.stream.wait_stream(torch.cuda.current_stream(dev))      # the uploaded state is visible to the side stream
+        self.head = self.tail = 0
+
+    def start(self):
+        self._enqueue()
+        return self
+
+    def _enqueue(self):
+        b = self.head & 1
+        self.stream.wait_event(self.free[b])
+        with torch.cuda.stream(self.stream):
+            self.mb.draw(self.B_total, self.buf[b], self.lo, self.n)
+            self.ready[b].record(self.stream)
+        self.head += 1
+
+    def take(self):
+        """Indices of the current step; the draw of the following step starts right away on the side stream."""
+        b = self.tail & 1
+        torch.cuda.current_stream(self.mb.device).wait_event(self.ready[b])
+        self._enqueue()
+        return self.buf[b]
+
+    def done_with(self, idx):
+        self.free[self.tail & 1].record(torch.cuda.current_stream(self.mb.device))
+        self.tail += 1
+
+    def finish(self):
+        """Make the main stream wait for the outstanding look-ahead draw (it has already advanced the generator)."""
+        torch.cuda.current_stream(self.mb.device).wait_stream(self.stream)
+
+
 class MinibatchPipeline:
     """Double-buffered host -> device staging of minibatch index arrays on a copy stream.
 

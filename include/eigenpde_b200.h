@@ -165,6 +165,18 @@ int epde_forward(const epde_desc* desc, const float* d_X, const int64_t* d_idx, 
  */
 int epde_minibatch_indices(uint32_t* h_mt, int32_t* h_pos, int64_t K, int64_t B, int64_t* h_idx_out);
 
+/*
+ * The same stream generated ON THE DEVICE (src/data_set.py:31,67,77): d_state holds the generator
+ * as 625 uint32 (624 state words + the position, i.e. random.getstate()[1]); the call consumes 2 * B_total words,
+ * writes the indices of draws [out_lo, out_lo + out_n) to d_idx[0 .. out_n) -- a rank of a sharded step passes its slice
+ * of the global batch, every rank advances the whole stream -- and leaves the advanced state in d_state exactly as CPython
+ * would show it after the same draws.  d_raw: scratch of 2 * B_total uint32 (8-byte aligned).  Asynchronous on `stream`;
+ * the generator itself is one CTA (the recurrence is sequential: 623 words per synchronisation, about 0.2 ms per 2^20
+ * draws), so callers overlap it with the previous step on a second stream.
+ */
+int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total, int64_t out_lo, int64_t out_n,
+                                  uint32_t* d_raw, int64_t* d_idx, void* stream);
+
 /* CPython random.seed(int) -> MT19937 state (init_by_array over the 32-bit words of |seed|);
  * `h_key` holds the little-endian 32-bit words of the absolute seed. */
 int epde_mt_seed(const uint32_t* h_key, int32_t key_len, uint32_t* h_mt, int32_t* h_pos);
