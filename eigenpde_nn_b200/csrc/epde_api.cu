@@ -205,7 +205,8 @@ int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, 
 }
 
 // ---- one-shot all-reduce over NVLink peer memory (the two tiny exchanges of the sharded step) --------------------------
-// Every rank owns one symmetric buffer [256 B of flags | 2 parities x world slots x slot_bytes].  A call (epoch e, parity
+// Every rank owns one symmetric buffer [256 B of flags = 2 parities x 32 ranks x uint32 | 2 parities x world slots x
+// slot_bytes]; world <= 32 (the flag block holds exactly 2 x 32 flags).  A call (epoch e, parity
 // e & 1) stores this rank's payload into slot[rank] of EVERY rank's buffer with plain peer stores, fences, raises
 // flag[parity][rank] = e in every rank's buffer, waits until all world flags of its OWN buffer show e, and sums the world
 // slots in rank order (the same order on every rank: bit-identical results everywhere).  A rank cannot run two epochs
@@ -393,10 +394,10 @@ int epde_minibatch_indices(uint32_t* mt, int32_t* pos, int64_t K, int64_t B, int
 int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total, int64_t out_lo, int64_t out_n,
                                   uint32_t* d_raw, int64_t* d_idx, void* stream) {
   if (!d_state || !d_raw || (!d_idx && out_n > 0)) return EPDE_ERR_NULL;
-  if (K < 1 || B_total < 0 || out_lo < 0 || out_n < 0 || out_lo + out_n > B_total) return EPDE_ERR_ARG;
+  if (K < 1 || B_total < 0 || B_total >= (1ll << 30) || out_lo < 0 || out_n < 0 || out_lo + out_n > B_total) return EPDE_ERR_ARG;
   if (((uintptr_t)d_raw & 7) || ((uintptr_t)d_state & 3)) return EPDE_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, 2 * B_total, d_raw);
+  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, (int)(2 * B_total), d_raw);
   if (out_n > 0) k_mt_to_idx<<<(unsigned)((out_n + 255) / 256), 256, 0, st>>>(d_raw, K, out_lo, out_n, d_idx);
   return (int)cudaGetLastError();
 }
@@ -484,7 +485,7 @@ __global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict
 int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
                         int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
   if (!d_peer_bufs || !src || !dst) return EPDE_ERR_NULL;
-  if (world < 1 || world > 64 || rank < 0 || rank >= world || n < 1 || epoch == 0 ||
+  if (world < 1 || world > 32 || rank < 0 || rank >= world || n < 1 || epoch == 0 ||
       n * (is_f64 ? 8 : 4) > slot_bytes || (slot_bytes & 15)) return EPDE_ERR_ARG;
   char* const* bufs = reinterpret_cast<char* const*>(d_peer_bufs);
   if (is_f64) k_peer_allreduce<double><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, (const double*)src, (double*)dst, (int)n, slot_bytes);

@@ -30,51 +30,54 @@ __host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// state[0..623] = mt, state[624] = pos (0..624).  Consumes W = 2 * B words starting at position pos of the current block
-// and writes them (untempered) to raw[0..W).  One CTA of MT_THREADS threads.
+// state[0..623] = mt, state[624] = pos (0..624).  Consumes W = 2 * B words (W < 2^31) starting at position pos of the
+// current block and writes them (untempered) to raw[0..W).  One CTA of MT_THREADS threads; 32-bit index arithmetic and
+// warp-uniform branches only (the CTA is issue-bound: 20 warps on one SM).
 __global__ void __launch_bounds__(MT_THREADS, 1)
-k_mt_generate(uint32_t* __restrict__ state, int64_t W, uint32_t* __restrict__ raw) {
+k_mt_generate(uint32_t* __restrict__ state, int W, uint32_t* __restrict__ raw) {
   __shared__ uint32_t buf[MT_N + MT_STEP * MT_CHUNK];
   const int tid = threadIdx.x;
-  const int64_t p0 = (int64_t)state[MT_N];
+  const int p0 = (int)state[MT_N];
   for (int i = tid; i < MT_N; i += MT_THREADS) buf[i] = state[i];
   __syncthreads();
   if (W <= 0) return;
-  const int64_t last = p0 + W - 1;                    // index (relative to the current block) of the last consumed word
-  const int64_t blk_f = last / MT_N;                  // block that becomes the new state
-  const int64_t sbase = blk_f * MT_N;
+  const long long last = (long long)p0 + W - 1;       // index (relative to the current block) of the last consumed word
+  const long long blk_f = last / MT_N;                // block that becomes the new state
   // words of the current block that the draws consume
-  for (int64_t x = p0 + tid; x < MT_N && x <= last; x += MT_THREADS) raw[x - p0] = buf[x];
+  for (int x = p0 + tid; x < MT_N && x <= last; x += MT_THREADS) raw[x - p0] = buf[x];
   if (blk_f > 0) {
-    const int64_t need_end = sbase + MT_N;            // generate x[624 .. need_end)
-    int64_t n = MT_N;                                 // frontier: x[n] is the next word to generate; buf[0] holds x[n - 624 - 623 * s]
-    while (n < need_end) {
-      int s = 0;
-      for (; s < MT_CHUNK && n < need_end; s++, n += MT_STEP) {
-        const uint32_t* h = buf + MT_STEP * s;        // h[i] = x[n - 624 + i]
-        if (tid < MT_STEP) {
-          const int j = tid;
-          const uint32_t* q = h + j;                  // q[i] = x[m - 624 + i], m = n + j
+    const long long nsteps = (blk_f * MT_N + MT_N - MT_N + MT_STEP - 1) / MT_STEP;   // steps until the frontier passes the end of block blk_f
+    // per-thread running indices (all fit 32 bits: W < 2^31): r = index into raw of the word this thread generates next,
+    // q = its index inside the final block (valid when 0 <= q < 624)
+    int r = MT_N + tid - p0;
+    long long qq = (long long)MT_N + tid - blk_f * MT_N;
+    const bool act = tid < MT_STEP;
+    for (long long s0 = 0; s0 < nsteps; s0 += MT_CHUNK) {
+      const int ns = (int)((nsteps - s0) < MT_CHUNK ? (nsteps - s0) : MT_CHUNK);
+      const bool tail = qq + (long long)MT_STEP * ns + MT_STEP > 0;      // warp-uniform enough: this chunk may touch the final block
+      for (int s = 0; s < ns; s++) {
+        if (act) {
+          const uint32_t* q = buf + MT_STEP * s + tid;     // q[i] = x[m - 624 + i], m = the word this thread generates
           uint32_t v;
-          if (j < 227)       v = q[397] ^ mt_f(q[0], q[1]);
-          else if (j < 454)  v = q[170] ^ mt_f(q[-227], q[-226]) ^ mt_f(q[0], q[1]);
-          else               v = q[-57] ^ mt_f(q[-454], q[-453]) ^ mt_f(q[-227], q[-226]) ^ mt_f(q[0], q[1]);
-          buf[MT_N + MT_STEP * s + j] = v;
-          const int64_t m = n + j;
-          if (m >= p0 && m <= last) raw[m - p0] = v;
-          if (m >= sbase && m < need_end) state[m - sbase] = v;
+          if (tid < 227)       v = q[397] ^ mt_f(q[0], q[1]);
+          else if (tid < 454)  v = q[170] ^ mt_f(q[-227], q[-226]) ^ mt_f(q[0], q[1]);
+          else                 v = q[-57] ^ mt_f(q[-454], q[-453]) ^ mt_f(q[-227], q[-226]) ^ mt_f(q[0], q[1]);
+          buf[MT_N + MT_STEP * s + tid] = v;
+          if ((unsigned)r < (unsigned)W) raw[r] = v;
+          if (tail && qq >= 0 && qq < MT_N) state[qq] = v;
         }
+        r += MT_STEP; qq += MT_STEP;
         __syncthreads();
       }
-      // compaction: keep the 624 words below the frontier, x[n - 624 .. n) = buf[623 s .. 623 s + 624)
+      // compaction: keep the 624 words below the frontier, buf[623 ns .. 623 ns + 624)
       uint32_t keep = 0;
-      if (tid < MT_N) keep = buf[MT_STEP * s + tid];
+      if (tid < MT_N) keep = buf[MT_STEP * ns + tid];
       __syncthreads();
       if (tid < MT_N) buf[tid] = keep;
       __syncthreads();
     }
   }
-  if (tid == 0) state[MT_N] = (uint32_t)(p0 + W - sbase);
+  if (tid == 0) state[MT_N] = (uint32_t)(last + 1 - blk_f * MT_N);
 }
 
 // idx[i] = min(floor(u * K), K - 1) for draws out_lo + i, i < out_n, from the raw words of k_mt_generate

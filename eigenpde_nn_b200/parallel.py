@@ -57,7 +57,7 @@ class PeerExchange:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             world, rank = dist.get_world_size(group), dist.get_rank(group)
-            if world < 2 or world > 64 or dist.get_backend(group) != "nccl":
+            if world < 2 or world > 32 or dist.get_backend(group) != "nccl":      # the flag block holds 2 x 32 flags
                 if os.environ.get("EPDE_EXCHANGE_DEBUG"):
                     print("[eigenpde_nn_b200] peer exchange not used: world", world, "backend", dist.get_backend(group))
                 return None

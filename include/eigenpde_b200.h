@@ -213,7 +213,7 @@ int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_g
  * d_peer_bufs: DEVICE array of `world` pointers, entry p = rank p's symmetric buffer mapped into this process
  * (e.g. torch.distributed._symmetric_memory: rendezvous(...).buffer_ptrs_dev); every buffer is
  * 256 + 2 * world * slot_bytes bytes and zero-filled before the first call.  epoch = 1, 2, 3, ... must advance by one
- * per call on every rank.  In place (src == dst) is allowed.  A peer that never arrives traps after about a minute.
+ * per call on every rank; world <= 32 (the 256-byte flag block holds 2 parities x 32 flags).  In place (src == dst) is allowed.  A peer that never arrives traps after about a minute.
  */
 int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
                         int64_t n, int is_f64, int64_t slot_bytes, void* stream);

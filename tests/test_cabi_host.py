@@ -171,6 +171,7 @@ def test_argument_validation_of_the_newer_entry_points(L):
     assert L.epde_peer_allreduce(one, 2, 2, 1, one, one, 13, 1, 65536, null) == -6
     assert L.epde_peer_allreduce(one, 0, 2, 1, one, one, 9000, 1, 65536, null) == -6
     assert L.epde_peer_allreduce(one, 0, 2, 1, one, one, 13, 1, 65530, null) == -6
+    assert L.epde_peer_allreduce(one, 0, 33, 1, one, one, 13, 1, 65536, null) == -6           # flag block holds 2 x 32 flags
     # epde_md_align: NULL pointers, too many atoms, reference index out of range
     ref = (C.c_double * 9)(*([0.0] * 9)); ri = (C.c_int32 * 3)(0, 1, 2); bad = (C.c_int32 * 3)(0, 1, 11)
     assert L.epde_md_align(10, 10, 32, null, ref, ri, 3, one, one, null, null) == -1
