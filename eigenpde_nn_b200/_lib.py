@@ -23,7 +23,7 @@ ABI_VERSION = 3
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
            "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
-           "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_peer_allreduce"]
+           "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_train_epilogue64", "epde_peer_allreduce", "epde_peer_allreduce_graph"]
 
 
 class EpdeDesc(C.Structure):
@@ -66,6 +66,8 @@ def lib():
         L.epde_eig_stats_accumulate.argtypes = [dp, vp, vp, vp]
         L.epde_peer_allreduce.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, vp, vp, i64, C.c_int, i64, vp]
         L.epde_train_epilogue.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.epde_train_epilogue64.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.epde_peer_allreduce_graph.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, i64, C.c_int, i64, vp]
         L.epde_md_align.argtypes = [i64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp]
         for name in EXPORTS:
             if name != "epde_error_string":

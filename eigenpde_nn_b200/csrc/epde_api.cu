@@ -213,8 +213,11 @@ int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, 
 // ahead of a peer (it needs that peer's flag for e+1, raised only after the peer finished e), so two parities suffice.
 template <typename T>
 __global__ void __launch_bounds__(1024)
-k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t epoch, const T* __restrict__ src,
-                 T* __restrict__ dst, int n, int64_t slot_bytes) {
+k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t epoch_arg, uint32_t* __restrict__ epoch_ctr,
+                 const T* __restrict__ src, T* __restrict__ dst, int n, int64_t slot_bytes) {
+  // epoch: an argument, or (epoch_ctr != NULL) a counter in device memory that every call advances by one -- the launch
+  // arguments are then invariant and the exchange can sit inside a replayed CUDA graph
+  const uint32_t epoch = epoch_ctr ? *epoch_ctr + 1u : epoch_arg;
   const int par = epoch & 1;
   const int64_t data_off = 256 + ((int64_t)par * world + rank) * slot_bytes;
   for (int p = 0; p < world; p++) {
@@ -239,6 +242,7 @@ k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t e
     for (int p = 0; p < world; p++) v += reinterpret_cast<const volatile T*>(base + (int64_t)p * slot_bytes)[i];
     dst[i] = v;
   }
+  if (epoch_ctr && threadIdx.x == 0) *epoch_ctr = epoch;      // every thread read it before the first __syncthreads
 }
 
 }  // namespace
@@ -467,6 +471,35 @@ k_epilogue(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   if (threadIdx.x == 0) state[1] = step;
 }
 
+// The same epilogue with fp64 master parameters and fp64 Adam moments (what the reference's `model.double()` +
+// torch.optim.Adam hold, src/pytorch_eigen_solver.py:374-379): the fp32 copy p32 is what the next step's kernels read.
+// torch's update order: m.lerp_(g, 1 - b1); v = b2 v + (1 - b2) g g; denom = sqrt(v) / sqrt(1 - b2^t) + eps;
+// p -= (lr / (1 - b1^t)) m / denom.
+__global__ void __launch_bounds__(1024)
+k_epilogue64(double* __restrict__ p, float* __restrict__ p32, const float* __restrict__ g, double* __restrict__ m,
+             double* __restrict__ v, int64_t n, double* __restrict__ state, double* __restrict__ avg,
+             double* __restrict__ stats, const double* __restrict__ out, int k) {
+  const double lr = state[0], step = state[1] + 1.0;
+  const double bc1 = 1.0 - pow(0.9, step), bc2s = sqrt(1.0 - pow(0.999, step));
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double gi = (double)g[i];
+    const double mi = m[i] + (gi - m[i]) * (1.0 - 0.9);
+    const double vi = v[i] * 0.999 + (1.0 - 0.999) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const double pi = p[i] - (lr / bc1) * (mi / (sqrt(vi) / bc2s + 1e-8));
+    p[i] = pi; p32[i] = (float)pi;
+  }
+  __syncthreads();
+  const int64_t per = n / k;
+  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = (int)(e / per);
+    const int src = (int)out[EPDE_OUT_CVEC(k) + i];
+    avg[e] += p[(int64_t)src * per + (e - (int64_t)i * per)];
+  }
+  if (threadIdx.x < k) { const double ev = out[EPDE_OUT_EIG(k) + threadIdx.x]; stats[threadIdx.x] += ev; stats[k + threadIdx.x] += ev * ev; }
+  if (threadIdx.x == 0) state[1] = step;
+}
+
 // averaged_model.nets[i] += model.nets[cvec[i]]  (record_model_parameters, src/pytorch_eigen_solver.py:114-118)
 __global__ void k_avg_acc(double* __restrict__ avg, const float* __restrict__ p, const double* __restrict__ out,
                           int k, int64_t per) {
@@ -482,15 +515,26 @@ __global__ void k_eig_stats(double* __restrict__ stats, const double* __restrict
   if (i < k) { const double e = out[EPDE_OUT_EIG(k) + i]; stats[i] += e; stats[k + i] += e * e; }
 }
 
-int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
-                        int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
+static int peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, uint32_t* d_epoch, const void* src,
+                          void* dst, int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
   if (!d_peer_bufs || !src || !dst) return EPDE_ERR_NULL;
-  if (world < 1 || world > 32 || rank < 0 || rank >= world || n < 1 || epoch == 0 ||
+  if (world < 1 || world > 32 || rank < 0 || rank >= world || n < 1 || (!d_epoch && epoch == 0) ||
       n * (is_f64 ? 8 : 4) > slot_bytes || (slot_bytes & 15)) return EPDE_ERR_ARG;
   char* const* bufs = reinterpret_cast<char* const*>(d_peer_bufs);
-  if (is_f64) k_peer_allreduce<double><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, (const double*)src, (double*)dst, (int)n, slot_bytes);
-  else k_peer_allreduce<float><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, (const float*)src, (float*)dst, (int)n, slot_bytes);
+  if (is_f64) k_peer_allreduce<double><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, d_epoch, (const double*)src, (double*)dst, (int)n, slot_bytes);
+  else k_peer_allreduce<float><<<1, 1024, 0, (cudaStream_t)stream>>>(bufs, rank, world, epoch, d_epoch, (const float*)src, (float*)dst, (int)n, slot_bytes);
   return (int)cudaGetLastError();
+}
+
+int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
+                        int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
+  return peer_allreduce(d_peer_bufs, rank, world, epoch, nullptr, src, dst, n, is_f64, slot_bytes, stream);
+}
+
+int epde_peer_allreduce_graph(void* const* d_peer_bufs, int rank, int world, uint32_t* d_epoch, const void* src, void* dst,
+                              int64_t n, int is_f64, int64_t slot_bytes, void* stream) {
+  if (!d_epoch) return EPDE_ERR_NULL;
+  return peer_allreduce(d_peer_bufs, rank, world, 0, d_epoch, src, dst, n, is_f64, slot_bytes, stream);
 }
 
 int epde_md_align(int64_t K, int32_t n_atoms, int32_t d_pad, const float* X, const double* ref_x, const int32_t* ref_index,
@@ -513,6 +557,14 @@ int epde_train_epilogue(const epde_desc* D, float* params, const float* grad, fl
   int rc = check_desc(D); if (rc) return rc;
   if (!params || !grad || !m || !v || !state || !avg || !stats || !out) return EPDE_ERR_NULL;
   k_epilogue<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, m, v, param_count(D), state, avg, stats, out, D->k);
+  return (int)cudaGetLastError();
+}
+
+int epde_train_epilogue64(const epde_desc* D, double* params64, float* params32, const float* grad, double* m, double* v,
+                          double* state, double* avg, double* stats, const double* out, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!params64 || !params32 || !grad || !m || !v || !state || !avg || !stats || !out) return EPDE_ERR_NULL;
+  k_epilogue64<<<1, 1024, 0, (cudaStream_t)stream>>>(params64, params32, grad, m, v, param_count(D), state, avg, stats, out, D->k);
   return (int)cudaGetLastError();
 }
 

@@ -137,7 +137,9 @@ class eigen_solver():
                 np.asarray(res["penalty"]))
 
     def train(self):
-        if os.environ.get("EPDE_DEVICE_LOOP") == "1":
+        """Default: the device-resident loop (`train_device_resident`).  EPDE_HOST_LOOP=1 selects the loop below, which
+        mirrors the reference statement by statement (host fp64 torch.optim.Adam, `update_step` every iteration)."""
+        if os.environ.get("EPDE_HOST_LOOP") != "1":
             return self.train_device_resident()
         stage_index = 0
         log_f = open('./data/%s' % self.log_filename, 'w')
@@ -191,14 +193,14 @@ class eigen_solver():
         log_f.close()
 
     def train_device_resident(self):
-        """Opt-in (EPDE_DEVICE_LOOP=1) version of `train` (:250-318) with the same stages, files and log
-        lines, whose loop body stays on the GPU: fp32 Adam (epde_adam_step), cvec-ordered averaging
-        (epde_average_accumulate) and the eigenvalue running sums (epde_eig_stats_accumulate).  The host
-        draws the minibatch indices (same MT19937 stream) and only synchronises every print_every_step
-        and at stage ends.  Numerics: parameters and Adam moments are fp32 here (fp64 in the default
-        loop), so trajectories agree with the reference to fp32 round-off, not to 1e-5 after many steps."""
+        """`train` (:250-318) with the same stages, files and log lines, whose loop body stays on the GPU: the minibatch
+        draw (the reference's MT19937 stream, continued on the device from Python's `random` state and handed back at every
+        stage end), the loss+gradient step, Adam with fp64 master parameters and moments as in the reference (:374-379),
+        cvec-ordered averaging (:114-118, :284) and the eigenvalue running sums (:280-282) -- one CUDA graph per step.
+        The host only synchronises every print_every_step and at stage ends."""
         from eigenpde_nn_b200.engine import DeviceTrainer
         trainer = DeviceTrainer(self.engine, self.model)
+        self.device_trainer = trainer
         stage_index = 0
         log_f = open('./data/%s' % self.log_filename, 'w')
         for i in range(self.train_max_step):
@@ -211,8 +213,8 @@ class eigen_solver():
                     stage_index + 1, i, bsz, lr, alpha_val))
                 stage_index += 1
 
-            idx = self.dataset.draw_indices(bsz)
-            trainer.step(idx, lr, alpha_val)
+            trainer.step(bsz, lr, alpha_val)
+            self.dataset.batch_size = bsz
 
             if i + 1 == self.stage_list[stage_index] or i + 1 == self.train_max_step:
                 tot_step_in_stage = i + 1 - self.stage_list[stage_index - 1]
@@ -225,6 +227,7 @@ class eigen_solver():
                 for ii in range(self.k):
                     print('  %dth eig:  mean=%.4f, var=%.4f' % (ii + 1, mean_eig_vals[ii],
                                                                math.sqrt(max(var_eig_vals[ii], 0.0))))
+                trainer.mb.sync_to_python()           # Python's `random` is where the reference would have left it
                 trainer.download(self.model, "params")
                 self.zero_model_parameters(self.model_bak)
                 self.copy_model_to_bak(cvec)

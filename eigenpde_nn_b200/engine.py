@@ -79,6 +79,9 @@ class StepEngine:
             self.grad = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
         self._ws = None
         self._ws_B = 0
+        self.ws_generation = 0          # bumped whenever the step workspace is re-allocated (captured graphs hold its address)
+        self._fws = None                # separate workspace of forward(): a stage-end full-data pass never moves the step's
+        self._fws_B = 0
         self._exchange = None
         if self.pg is not None:
             from .parallel import PeerExchange
@@ -92,9 +95,20 @@ class StepEngine:
             _lib.check(self.lib.epde_workspace_bytes(C.byref(self.desc), B, C.byref(need)), "epde_workspace_bytes")
             self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
             self._ws_B = B
+            self.ws_generation += 1
             off = (-self._ws.data_ptr()) % 256
             self._ws_view = self._ws[off:off + need.value]
         return self._ws_view
+
+    def _forward_workspace(self, B):
+        if self._fws is None or B > self._fws_B:
+            need = C.c_size_t()
+            _lib.check(self.lib.epde_workspace_bytes(C.byref(self.desc), B, C.byref(need)), "epde_workspace_bytes")
+            self._fws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
+            self._fws_B = B
+            off = (-self._fws.data_ptr()) % 256
+            self._fws_view = self._fws[off:off + need.value]
+        return self._fws_view
 
     def flat_params(self, model) -> torch.Tensor:
         """fp32 flat copy of model.parameters() (the reference keeps them in fp64, :374)."""
@@ -147,7 +161,7 @@ class StepEngine:
                     var=h[4 + 3 * k:4 + 4 * k].copy(), grad=grad)
 
     def forward(self, idx_dev, B, params_dev):
-        ws = self._workspace(max(min(B, 262144), 1))
+        ws = self._forward_workspace(max(min(B, 262144), 1))
         y = torch.empty((B, self.k), dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self.lib.epde_forward(C.byref(self.desc), _ptr(self.X), _ptr(idx_dev), C.c_int64(B),
@@ -355,17 +369,21 @@ def md_align(X, ref_x, ref_index, diag_coeff, device=None, want_metric=True):
 
 class DeviceTrainer:
     """Device-resident version of the per-step loop body of `eigen_solver.train`
-    (src/pytorch_eigen_solver.py:277-284): loss+gradient step, Adam (torch.optim.Adam defaults, fp32),
-    model averaging in cvec order and the eigenvalue running sums all stay on the GPU; the host only
-    draws the minibatch indices and enqueues.  Nothing is synchronised until `read_scalars()` /
-    `download()` is called (every print_every_step / at a stage end)."""
+    (src/pytorch_eigen_solver.py:277-284): minibatch draw (the reference's MT19937 stream, DeviceMinibatch), loss+gradient
+    step, Adam, model averaging in cvec order and the eigenvalue running sums all stay on the GPU and are replayed as ONE
+    CUDA graph per (batch size, alpha).  Like the reference, the master parameters and the Adam moments are fp64
+    (`model.double()` :374, torch.optim.Adam :379); the step's kernels read an fp32 copy refreshed by the epilogue.
+    Nothing is synchronised until `read_scalars()` / `download()` is called (every print_every_step / at a stage end).
+    With a process group every rank draws the global batch, keeps its slice, and the two exchanges (NVLink peer-memory
+    kernel) are part of the graph."""
 
-    def __init__(self, engine: StepEngine, model, use_graph=None):
+    def __init__(self, engine: StepEngine, model, use_graph=None, minibatch=None):
         self.e = engine
         dev = engine.device
-        self.p = engine.flat_params(model)
-        self.m = torch.zeros_like(self.p)
-        self.v = torch.zeros_like(self.p)
+        self.p64 = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).to(device=dev, dtype=torch.float64)
+        self.p = self.p64.to(torch.float32)
+        self.m = torch.zeros_like(self.p64)
+        self.v = torch.zeros_like(self.p64)
         self.avg = torch.zeros(engine.n_params, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(2 * engine.k, dtype=torch.float64, device=dev)
         # [learning rate, optimiser steps taken so far] in device memory: the step's launches then have constant
@@ -374,11 +392,16 @@ class DeviceTrainer:
         self._lr = None
         self.steps_in_stage = 0
         self._idx_dev = None
-        self._pin, self._pin_ev, self._pin_i = [], [], 0
+        self.mb = minibatch if minibatch is not None else DeviceMinibatch(engine.K, dev, engine.lib).seed_from_python()
+        self.world, self.rank = 1, 0
+        if engine.pg is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(engine.pg), dist.get_rank(engine.pg)
         if use_graph is None:
             import os
             use_graph = os.environ.get("EPDE_GRAPH", "1") != "0"
-        self.use_graph = bool(use_graph) and engine.pg is None      # the multi-rank step runs NCCL between the phases
+        # NCCL collectives between the phases are not captured; the peer-memory exchange is a plain kernel and is
+        self.use_graph = bool(use_graph) and (engine.pg is None or engine._exchange is not None)
         self._graph, self._graph_key, self._seen_key = None, None, None
 
     def start_stage(self):
@@ -387,33 +410,33 @@ class DeviceTrainer:
         self.steps_in_stage = 0
 
     def _launch(self, B, alpha):
+        from .parallel import shard_bounds
         e = self.e
-        out, grad = e.step_device(self._idx_dev, B, self.p, alpha)
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        self.mb.draw(B, self._idx_dev, lo, hi - lo)            # every rank advances the global stream, keeps its slice
+        out, grad = e.step_device(self._idx_dev, hi - lo, self.p, alpha)
         st = C.c_void_p(torch.cuda.current_stream(e.device).cuda_stream)
         # Adam, then the averaging with the UPDATED parameters (:277, :284), then the eigenvalue running sums
-        _lib.check(e.lib.epde_train_epilogue(C.byref(e.desc), _ptr(self.p), _ptr(grad), _ptr(self.m), _ptr(self.v),
-                                             _ptr(self.state), _ptr(self.avg), _ptr(self.stats), _ptr(out), st),
-                   "epde_train_epilogue")
+        _lib.check(e.lib.epde_train_epilogue64(C.byref(e.desc), _ptr(self.p64), _ptr(self.p), _ptr(grad), _ptr(self.m),
+                                               _ptr(self.v), _ptr(self.state), _ptr(self.avg), _ptr(self.stats), _ptr(out),
+                                               st), "epde_train_epilogue64")
 
-    def step(self, idx, lr, alpha):
+    def step(self, B, lr, alpha):
+        """One training step with a GLOBAL batch of B samples drawn on the device."""
+        from .parallel import shard_bounds
         e = self.e
-        B = len(idx)
+        B = int(B)
         alpha = float(alpha)
-        if self._idx_dev is None or self._idx_dev.numel() != B:
-            self._idx_dev = torch.empty(B, dtype=torch.int64, device=e.device)
-            self._pin = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(4)]
-            self._pin_ev = [None] * 4
+        lo, hi = shard_bounds(B, self.world, self.rank)
+        if self._idx_dev is None or self._idx_dev.numel() != hi - lo:
+            self._idx_dev = torch.empty(hi - lo, dtype=torch.int64, device=e.device)
             self._graph = self._graph_key = self._seen_key = None
         if lr != self._lr:
             self.state[0:1].fill_(float(lr))
             self._lr = lr
-        j = self._pin_i = (self._pin_i + 1) & 3
-        if self._pin_ev[j] is not None:
-            self._pin_ev[j].synchronize()                    # the upload that last used this pinned buffer is done
-        self._pin[j].numpy()[:] = idx
-        self._idx_dev.copy_(self._pin[j], non_blocking=True)
-        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(e.device)); self._pin_ev[j] = ev
-        key = (B, alpha)
+        key = (B, alpha, e.ws_generation)
+        if self._graph_key is not None and self._graph_key[:2] == key[:2] and self._graph_key[2] != e.ws_generation:
+            self._graph = self._graph_key = self._seen_key = None     # the workspace moved: the captured addresses are stale
         if not self.use_graph:
             self._launch(B, alpha)
         elif self._graph_key == key:
@@ -426,7 +449,7 @@ class DeviceTrainer:
             g.replay()
         else:                                                # first step: eager (allocates the workspace, sets attributes)
             self._launch(B, alpha)
-            self._seen_key = key
+            self._seen_key = (B, alpha, e.ws_generation)
         self.steps_in_stage += 1
 
     @property
@@ -442,7 +465,7 @@ class DeviceTrainer:
 
     def download(self, model, source="params"):
         """Copy the device parameters (or the accumulated average) into a host MyNet."""
-        flat = (self.p.double() if source == "params" else self.avg).cpu()
+        flat = (self.p64 if source == "params" else self.avg).cpu()
         off = 0
         with torch.no_grad():
             for prm in model.parameters():

@@ -44,8 +44,11 @@ class PeerExchange:
     SLOT_BYTES = 64 * 1024          # per rank and parity; larger vectors go through NCCL
 
     def __init__(self, lib, hdl, buf, rank, world):
+        import torch
         self.lib, self.hdl, self.buf, self.rank, self.world = lib, hdl, buf, rank, world
-        self.epoch = 0
+        # the call counter (epoch) lives in device memory and is advanced by the kernel itself: the launch arguments never
+        # change, so the exchanges can be captured into a CUDA graph together with the step's kernels
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=buf.device)
 
     @classmethod
     def create(cls, lib, group, device):
@@ -83,10 +86,10 @@ class PeerExchange:
         import torch
         from . import _lib
         assert t.is_contiguous() and t.dtype in (torch.float32, torch.float64) and self.fits(t)
-        self.epoch += 1
         st = C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
-        _lib.check(self.lib.epde_peer_allreduce(C.c_void_p(self.hdl.buffer_ptrs_dev), self.rank, self.world,
-                                                C.c_uint32(self.epoch), C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()),
-                                                C.c_int64(t.numel()), 1 if t.dtype == torch.float64 else 0,
-                                                C.c_int64(self.SLOT_BYTES), st), "epde_peer_allreduce")
+        _lib.check(self.lib.epde_peer_allreduce_graph(C.c_void_p(self.hdl.buffer_ptrs_dev), self.rank, self.world,
+                                                      C.c_void_p(self.epoch_dev.data_ptr()), C.c_void_p(t.data_ptr()),
+                                                      C.c_void_p(t.data_ptr()), C.c_int64(t.numel()),
+                                                      1 if t.dtype == torch.float64 else 0, C.c_int64(self.SLOT_BYTES), st),
+                   "epde_peer_allreduce_graph")
         return t

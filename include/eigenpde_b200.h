@@ -206,6 +206,14 @@ int epde_eig_stats_accumulate(const epde_desc* desc, double* d_stats, const doub
  */
 int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_grad, float* d_m, float* d_v,
                         double* d_state, double* d_avg, double* d_stats, const double* d_out_scalars, void* stream);
+/*
+ * The same with fp64 master parameters and fp64 Adam moments -- what the reference holds (`model.double()` :374-376,
+ * torch.optim.Adam :379): d_params64 is updated in fp64 with torch's update order, d_params32 receives the fp32 copy
+ * the next step's kernels read, d_avg accumulates the fp64 parameters in cvec order (:114-118).
+ */
+int epde_train_epilogue64(const epde_desc* desc, double* d_params64, float* d_params32, const float* d_grad,
+                          double* d_m, double* d_v, double* d_state, double* d_avg, double* d_stats,
+                          const double* d_out_scalars, void* stream);
 
 /*
  * One-shot all-reduce (sum) of a small vector over NVLink peer memory, for the two exchanges of the sharded step
@@ -217,6 +225,10 @@ int epde_train_epilogue(const epde_desc* desc, float* d_params, const float* d_g
  */
 int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
                         int64_t n, int is_f64, int64_t slot_bytes, void* stream);
+/* The same with the epoch kept in device memory (*d_epoch, zero before the first call, advanced by one per call): the
+ * launch arguments never change, so the exchange can be captured into a CUDA graph with the rest of the step. */
+int epde_peer_allreduce_graph(void* const* d_peer_bufs, int rank, int world, uint32_t* d_epoch, const void* src, void* dst,
+                              int64_t n, int is_f64, int64_t slot_bytes, void* stream);
 
 /*
  * MD pre-processing layer `MD_data_set.align` (src/data_set.py:126-153; called from every net's forward,

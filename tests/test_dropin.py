@@ -107,16 +107,17 @@ def test_constructor_matches_reference_contract(dropin, tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("device_loop", [False, True])
+@pytest.mark.parametrize("device_loop", [True, False], ids=["default_device_loop", "host_loop"])
 def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch, device_loop):
-    """Same seed, same data file: 10 Adam steps over two stages.  The reference log is fp64 CPU;
-    ours is the fp32 CUDA step + the same fp64 host Adam, so the trajectories agree to ~1e-5.
-    device_loop=True runs the opt-in device-resident loop (fp32 Adam, averaging and eigenvalue
-    statistics on the GPU, EPDE_DEVICE_LOOP=1) against the same reference log and checkpoints."""
+    """Same seed, same data file: 10 Adam steps over two stages.  The reference log is fp64 CPU; ours is the fp32
+    CUDA step with fp64 master parameters / Adam moments, so the trajectories agree to ~1e-5.
+    device_loop=True is the DEFAULT `train()`: minibatch draw, step, fp64 Adam, averaging and eigenvalue statistics in
+    one CUDA graph per step; False (EPDE_HOST_LOOP=1) is the statement-by-statement mirror of the reference's loop.
+    Both are held to the same tolerance against the same reference log and checkpoints."""
     if device_loop:
-        monkeypatch.setenv("EPDE_DEVICE_LOOP", "1")
+        monkeypatch.delenv("EPDE_HOST_LOOP", raising=False)
     else:
-        monkeypatch.delenv("EPDE_DEVICE_LOOP", raising=False)
+        monkeypatch.setenv("EPDE_HOST_LOOP", "1")
     z = np.load(os.path.join(GOLDEN, "dropin_run.npz"))
     (tmp_path / "data").mkdir()
     with open(tmp_path / "data" / "states.txt", "w") as fh:
@@ -125,6 +126,13 @@ def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch, devic
     monkeypatch.chdir(tmp_path)
     solver = dropin.pes.eigen_solver(_param_namespace(), int(z["seed"]))
     solver.run()
+    # Python's `random` ends where the reference leaves it: 6 draws of 500 + 4 of 800 from random.seed(seed)
+    after = random.random()
+    random.seed(int(z["seed"]))
+    K = z["X"].shape[0]
+    for b in [500] * 6 + [800] * 4:
+        random.choices(range(K), cum_weights=np.arange(1, K + 1), k=b)
+    assert random.random() == after
     ref = np.array([[float(v) for v in line.split()] for line in str(z["log"]).strip().splitlines()])
     got = np.loadtxt(tmp_path / "data" / "log.txt", ndmin=2)
     assert got.shape == ref.shape == (10, 7)
@@ -141,12 +149,44 @@ def test_training_run_matches_reference_log(dropin, tmp_path, monkeypatch, devic
 
 
 @pytest.mark.gpu
+def test_equal_stages_replay_the_graph_across_a_stage_end_forward(dropin, tmp_path, monkeypatch):
+    """Two stages with the SAME (batch size, alpha) and K > B: the stage-end full-data forward
+    (update_mean_and_var_of_model) runs between two replays of the same CUDA graph.  It must not move the workspace the
+    graph captured (forward has its own; a re-allocation invalidates the graph) -- the device loop has to reproduce the
+    host loop on this schedule."""
+    z = np.load(os.path.join(GOLDEN, "dropin_run.npz"))
+    (tmp_path / "data").mkdir()
+    with open(tmp_path / "data" / "states.txt", "w") as fh:
+        fh.write("%d %d\n" % z["X"].shape)
+        np.savetxt(fh, np.concatenate([z["X"], z["w"][:, None]], axis=1), fmt="%.10f")
+    monkeypatch.chdir(tmp_path)
+    logs = {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            monkeypatch.setenv("EPDE_HOST_LOOP", "1")
+        else:
+            monkeypatch.delenv("EPDE_HOST_LOOP", raising=False)
+        P = _param_namespace()
+        P.stage_list, P.batch_size_list, P.learning_rate_list, P.alpha_list = [0, 5, 10], [400, 400], [5e-3, 5e-3], [20.0, 20.0]
+        assert z["X"].shape[0] > 400
+        solver = dropin.pes.eigen_solver(P, 31)
+        solver.run()
+        logs[mode] = np.loadtxt(tmp_path / "data" / "log.txt", ndmin=2)
+        if mode == "device":
+            assert solver.device_trainer._graph is not None                 # the graph path was actually taken
+    a, b = logs["device"], logs["host"]
+    assert a.shape == b.shape == (10, 7)
+    scale = np.maximum(np.abs(b[:, 1:]), 1e-2 * np.abs(b[:, 1:2]))
+    assert (np.abs(a[:, 1:] - b[:, 1:]) / scale).max() < 1e-4
+
+
+@pytest.mark.gpu
 def test_md_mode_training_run_matches_reference_log(dropin, tmp_path, monkeypatch):
     """`md_data_flag=True`: the reference builds an `MD_data_set`, reads ./data/ref_state.txt and runs
     the Kabsch alignment layer inside every net's forward (training steps AND the stage-end full-data passes).  The
     drop-in evaluates the layer once per data set on the GPU (`epde_md_align`) and trains on the aligned rows with the
     per-row Jacobian metric: 8 Adam steps over two stages against the log and checkpoints of the unmodified reference."""
-    monkeypatch.delenv("EPDE_DEVICE_LOOP", raising=False)
+    monkeypatch.delenv("EPDE_HOST_LOOP", raising=False)
     monkeypatch.delenv("EPDE_MD_NO_ALIGN", raising=False)
     z = np.load(os.path.join(GOLDEN, "dropin_run_md.npz"))
     (tmp_path / "data").mkdir()

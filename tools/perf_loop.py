@@ -25,9 +25,9 @@ for i in range(steps): host_step(i)
 torch.cuda.synchronize(); t_host = (time.perf_counter() - t0) / steps
 tr = DeviceTrainer(eng, model)
 tr.start_stage()
-for i in range(10): tr.step(idxs[i % 16], 5e-3, 20.0)
+for i in range(10): tr.step(B, 5e-3, 20.0)
 torch.cuda.synchronize(); t0 = time.perf_counter()
-for i in range(steps): tr.step(idxs[i % 16], 5e-3, 20.0)
+for i in range(steps): tr.step(B, 5e-3, 20.0)
 torch.cuda.synchronize(); t_dev = (time.perf_counter() - t0) / steps
-print("B=%d: default loop %.3f ms/step (%.0f steps/s), device-resident loop %.3f ms/step (%.0f steps/s)"
+print("B=%d: host-Adam loop %.3f ms/step (%.0f steps/s), device-resident loop %.3f ms/step (%.0f steps/s)"
       % (B, t_host * 1e3, 1 / t_host, t_dev * 1e3, 1 / t_dev))
