@@ -76,6 +76,24 @@ def lib():
     return _lib
 
 
+TORCH_LIB_PATH = os.path.join(HERE, "libeigenpde_torch.so")
+_ops = None
+
+
+def torch_ops():
+    """torch.ops.epde (the PyTorch extension shim over the C ABI, csrc_torch/epde_torch.cpp), loaded on first use.
+    Raises if libeigenpde_torch.so has not been built -- like the C library it is never built implicitly."""
+    global _ops
+    if _ops is None:
+        import torch
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise EpdeError("%s not found: build it with `python -m eigenpde_nn_b200.build`" % TORCH_LIB_PATH)
+        lib()                                   # libeigenpde_b200.so first (the shim links against it)
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _ops = torch.ops.epde
+    return _ops
+
+
 def check(rc: int, what: str):
     if rc != 0:
         raise EpdeError("%s failed: %d (%s)" % (what, rc, lib().epde_error_string(rc).decode()))

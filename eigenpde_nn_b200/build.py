@@ -78,5 +78,32 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     return LIB
 
 
+TORCH_LIB = os.path.join(HERE, "libeigenpde_torch.so")
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """The PyTorch extension shim (csrc_torch/epde_torch.cpp: TORCH_LIBRARY ops over the C ABI) -> libeigenpde_torch.so,
+    in-tree, linked against libeigenpde_b200.so ($ORIGIN rpath) and the installed torch.  Plain g++: the shim has no kernels."""
+    src = os.path.join(HERE, "csrc_torch", "epde_torch.cpp")
+    hdr = os.path.join(os.path.dirname(HERE), "include", "eigenpde_b200.h")
+    if (not force and os.path.exists(TORCH_LIB)
+            and os.path.getmtime(TORCH_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB))):
+        return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = (["g++", "-O2", "-fPIC", "-shared", "-std=c++17",
+            "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI), src]
+           + ["-I" + i for i in ce.include_paths()] + ["-I/usr/local/cuda/include", "-L" + HERE, "-leigenpde_b200",
+              "-Wl,-rpath,$ORIGIN", "-L" + libdir, "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-Wl,-rpath," + libdir,
+              "-o", TORCH_LIB])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building %s" % TORCH_LIB)
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv))

@@ -87,6 +87,12 @@ class StepEngine:
             from .parallel import PeerExchange
             self._exchange = PeerExchange.create(self.lib, self.pg, self.device)
         self._eigw_c = (C.c_double * self.k)(*self.eig_w)
+        # the step is dispatched as a torch operator (torch.ops.epde.*: the extension shim over the C ABI, current-stream
+        # semantics by at::cuda::getCurrentCUDAStream); EPDE_BINDING=ctypes calls the C ABI directly instead
+        import os
+        self.ops = None if os.environ.get("EPDE_BINDING") == "ctypes" else _lib.torch_ops()
+        self._act_id = int(self.desc.act_id)
+        self._flags = int(self.desc.flags)
 
     # -- buffers ------------------------------------------------------------------------------
     def _workspace(self, B):
@@ -126,21 +132,35 @@ class StepEngine:
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         args = (C.byref(self.desc), _ptr(self.X), _ptr(self.w), _ptr(idx_dev), C.c_int64(B), _ptr(params_dev),
                 _ptr(self.diag))
+        ops = self.ops
         if self.pg is None:
-            _lib.check(self.lib.epde_step(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
-                                          _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), st),
-                       "epde_step")
+            if ops is not None:
+                ops.step(self.X, self.w, idx_dev, B, params_dev, self.diag, self.beta, float(alpha), self.eig_w, self.arch,
+                         self.k, self._act_id, self._flags, self.metric, ws, self.out, self.grad)
+            else:
+                _lib.check(self.lib.epde_step(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                              _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), st),
+                           "epde_step")
         else:
             from .parallel import two_phase_step
 
             def partial():
-                _lib.check(self.lib.epde_step_partial(*args, _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.sums), st),
-                           "epde_step_partial")
+                if ops is not None:
+                    ops.step_partial(self.X, self.w, idx_dev, B, params_dev, self.diag, self.arch, self.k, self._act_id,
+                                     self._flags, self.metric, ws, self.sums)
+                else:
+                    _lib.check(self.lib.epde_step_partial(*args, _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.sums), st),
+                               "epde_step_partial")
 
             def finish():
-                _lib.check(self.lib.epde_step_finish(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
-                                                     _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()),
-                                                     _ptr(self.out), _ptr(self.grad), st), "epde_step_finish")
+                if ops is not None:
+                    ops.step_finish(self.X, self.w, idx_dev, B, params_dev, self.diag, self.beta, float(alpha), self.eig_w,
+                                    self.arch, self.k, self._act_id, self._flags, self.metric, self.sums, ws, self.out,
+                                    self.grad)
+                else:
+                    _lib.check(self.lib.epde_step_finish(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                                         _ptr(self.sums), _ptr(ws), C.c_size_t(ws.numel()),
+                                                         _ptr(self.out), _ptr(self.grad), st), "epde_step_finish")
 
             two_phase_step(partial, finish, self.sums, self.grad, self.pg, self._exchange)
         return self.out, self.grad

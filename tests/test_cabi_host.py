@@ -181,3 +181,20 @@ def test_argument_validation_of_the_newer_entry_points(L):
     # epde_train_epilogue: descriptor and pointer checks
     desc = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
     assert L.epde_train_epilogue(C.byref(desc), null, one, one, one, one, one, one, one, null) == -1
+
+
+def test_torch_extension_shim_loads_and_mirrors_the_c_abi(L):
+    """libeigenpde_torch.so: TORCH_LIBRARY ops over the C ABI (north_star: "ships as a PyTorch C++/CUDA extension behind a
+    thin C-ABI").  Without a GPU only the host-side op can run; the schemas of the compute ops are checked."""
+    from eigenpde_nn_b200 import _lib, build
+    build.build_torch_ext()
+    ops = _lib.torch_ops()
+    desc = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
+    need = C.c_size_t()
+    assert L.epde_workspace_bytes(C.byref(desc), 4096, C.byref(need)) == 0
+    assert ops.workspace_bytes([50, 20, 20, 20, 1], 3, 0, 52, int(desc.flags), 4096) == need.value
+    for name in ("step", "step_partial", "step_finish"):
+        schema = str(getattr(ops, name).default._schema)
+        assert "Tensor X" in schema and "Tensor(a!) ws" in schema, schema
+    with pytest.raises(RuntimeError):
+        ops.workspace_bytes([50, 20, 20, 20, 1], 9, 0, 52, 1, 4096)          # k > EPDE_MAX_K: EPDE_ERR_DESC surfaces as an exception

@@ -189,6 +189,22 @@ def test_partial_finish_split_equals_two_shards():
     _check(c, _oracle(c), res)
 
 
+def test_torch_operator_and_ctypes_bindings_agree(monkeypatch):
+    """The step reaches the library through torch.ops.epde.* (extension shim, default) or through ctypes
+    (EPDE_BINDING=ctypes): same C ABI, bit-identical results; the default engine uses the torch operator."""
+    c = _rand_case(5, 50, 3, [20, 20, 20], 5000, 3001)
+    flat = _flat(c["params"])
+    e1 = _engine(c)
+    assert e1.ops is not None
+    a = e1.step(c["idx"], flat, c["alpha"]); ga = a["grad"].clone()
+    monkeypatch.setenv("EPDE_BINDING", "ctypes")
+    e2 = _engine(c)
+    assert e2.ops is None
+    b = e2.step(c["idx"], flat, c["alpha"])
+    assert a["loss"] == b["loss"] and torch.equal(ga, b["grad"])
+    _check(c, _oracle(c), a)
+
+
 def test_deterministic_bitwise():
     """Bit-identical results run to run with DEFAULT flags: every group of the tensor-core kernels owns its staging buffer
     and accumulators and adds its tiles in a fixed order, the group images are summed in a fixed order."""
