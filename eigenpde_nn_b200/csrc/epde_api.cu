@@ -141,8 +141,13 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
     e = cudaMemsetAsync(W.mx, 0, (size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4, st);     // maxima are gathered with atomicMax
     if (e != cudaSuccess) return (int)e;
   }
-  e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
-  if (e != cudaSuccess) return (int)e;
+  if (impl == 1) {
+    rc = tc::gather_pack(X, w, idx, B, D->d, D->d_pad, D->k, W.xt, W.wt, W.mx, params, diag, W.pwt, W.nrm, st);
+    if (rc) return rc;
+  } else {
+    e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, 0, nullptr);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (impl == 1)
     return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
                        W.mx, W.nrm, W.stash, st);
@@ -176,7 +181,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
     rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
     if (rc) return rc;
     const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
-    k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+    k_fin2<kFusedH><<<dim3(D->k, 24), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
     return (int)cudaGetLastError();
   }
   const int64_t ntiles = (B + P2_T - 1) / P2_T;

@@ -29,12 +29,13 @@ struct EigW { double v[EPDE_MAX_K]; };
 
 // Everything that depends only on the batch-global sums: eig_vals, cvec, losses
 // (src/pytorch_eigen_solver.py:215-229, 177-189) and the per-sample seed coefficients of the
-// reverse pass (SURVEY.md 8(a) closed form).  One thread; k <= 8.
+// reverse pass (SURVEY.md 8(a) closed form).  One thread (k <= 8); the staging bounds of the tensor-core family: one thread per net.
 template <int DUMMY = 0>
 __global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
                        double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx = nullptr,
                        const float* __restrict__ nrm = nullptr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x == 0) {
   const double W = sums[0];
   const double* S1 = sums + 1;
   const double* E = sums + 1 + k;
@@ -86,17 +87,24 @@ __global__ void k_coef(const double* __restrict__ sums, int k, double beta, doub
       }
       coef->cm[i] = (float)cmi;
     }
-    if (mx && nrm) {
+  }
+  __threadfence_block();        // the per-net bound computation below reads coef->ecoef / Cw / cm written here
+  }   // thread 0
+  __syncwarp();
+  if (coef && mx && nrm) {
       // a-priori bounds of every vector the gradient rounds stage (per net), from the measured maxima of the forward /
       // Jacobian quantities and the induced infinity norms of the weight matrices; 5 % slack for fp32 rounding
-      auto pow2 = [](double bound) -> double {        // s = 2^e with bound * s <= 2^14
-        if (!(bound > 0.0) || !isfinite(bound)) return 1.0;
-        int e; frexp(bound * 1.05, &e);
-        int q = 14 - e; q = q > 60 ? 60 : (q < -60 ? -60 : q);
-        return ldexp(1.0, q);
+      auto pow2 = [](double bound) -> double {        // s = 2^q with bound * 1.05 * s < 2^14
+        const float b = (float)(bound * 1.05);
+        if (!(b > 0.f) || !isfinite(b)) return 1.0;
+        int q = 14 - ((int)(__float_as_uint(b) >> 23) - 126);      // b in [2^(E-127), 2^(E-126))
+        q = q > 60 ? 60 : (q < -60 ? -60 : q);
+        return (double)__uint_as_float((uint32_t)(q + 127) << 23);
       };
       const double wmax = mx[0], xmax = fmax((double)mx[1], 1.0);
-      for (int i = 0; i < k; i++) {
+      {
+        const int i = threadIdx.x;                    // one thread per net
+        if (i < k) {
         const float* M = mx + 2 + kMxPerNet * i;
         const float* N = nrm + kNrmPerNet * i;
         const double g2m = M[0], g1m = M[1], tm = M[2], g3m = N[4];
@@ -117,8 +125,8 @@ __global__ void k_coef(const double* __restrict__ sums, int k, double beta, doub
         coef->fl[i][2] = (float)(1.0 / (s[2] * s[5])); coef->fl[i][3] = (float)(1.0 / (s[6] * s[10]));
         coef->fl[i][4] = (float)(1.0 / (s[7] * s[10])); coef->fl[i][5] = (float)(1.0 / (s[8] * s[10]));
         coef->fl[i][6] = (float)(1.0 / (s[9] * s[10])); coef->fl[i][7] = (float)(1.0 / (s[11] * s[12]));
+        }
       }
-    }
   }
 }
 

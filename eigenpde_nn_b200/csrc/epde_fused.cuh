@@ -143,14 +143,13 @@ k_gather(const float* __restrict__ X, const float* __restrict__ w, const int64_t
 // -> 8 CTAs = 64 warps per SM (k_gather: 4 CTAs = 32 warps), more row loads in flight for the DRAM-bound gather.
 // Output: xt[tile128][j][128] (one contiguous block per tile), wt[n].
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(256)
-k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
-            int d_pad, float* __restrict__ xt, float* __restrict__ wt, float* __restrict__ mx) {
+__device__ __forceinline__ void gather128_body(const float* __restrict__ X, const float* __restrict__ w,
+                                               const int64_t* __restrict__ idx, int64_t B, int d_pad, float* __restrict__ xt,
+                                               float* __restrict__ wt, float* __restrict__ mx, int64_t tile) {
   extern __shared__ float4 smem4[];
   float* ts = reinterpret_cast<float*>(smem4);           // [128][d_pad + 1]
   __shared__ int64_t srow[128];
   const int ld = d_pad + 1, nq = d_pad >> 2, t = threadIdx.x;
-  const int64_t tile = blockIdx.x;
   float mw = 0.f, mxv = 0.f;                               // max w, max |x| of the minibatch (bounds of phase 2's fp16 staging)
   if (t < 128) {
     const int64_t n = tile * 128 + t;
@@ -186,6 +185,12 @@ k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int6
   }
   float* out = xt + (size_t)tile * d_pad * 128 + (t & 127);
   for (int j = (t >> 7); j < d_pad; j += 2) out[(size_t)j * 128] = ts[(t & 127) * ld + j];
+}
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(256)
+k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B,
+            int d_pad, float* __restrict__ xt, float* __restrict__ wt, float* __restrict__ mx) {
+  gather128_body<DUMMY>(X, w, idx, B, d_pad, xt, wt, mx, (int64_t)blockIdx.x);
 }
 
 // layer 1: a1 = tanh(W1 x + b1); x_j of the sample pair is one coalesced float2 of the transposed

@@ -12,7 +12,11 @@ namespace tc {
 size_t pack_floats(int d);          // floats of one net's packed weight image
 size_t stash_floats(int64_t B, int k);   // floats of the phase-1 -> phase-2 stash (epde_tc_fused.cuh)
 
-// phase 1: k_pack_tc + k_pass1_tc + k_sums_y + k_reduce_tc -> sums[1 + 2k + k(k+1)/2], ybuf[B][k]
+// k_gather128_pack: minibatch rows -> tile-major transposed copy xt / wt (+ maxima), flat parameters -> packed weight images
+int gather_pack(const float* X, const float* w, const int64_t* idx, int64_t B, int d, int d_pad, int k, float* xt, float* wt,
+                float* mx, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st);
+
+// phase 1: k_pass1_tc + k_sums_y + k_reduce_tc -> sums[1 + 2k + k(k+1)/2], ybuf[B][k]
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
             float* stash, cudaStream_t st);

@@ -15,6 +15,17 @@ extern "C" int epde_debug_tc_cycles(unsigned long long* h16, int reset) {
 namespace epde {
 namespace tc {
 
+// minibatch gather (128-sample tiles) + weight packing in one launch
+int gather_pack(const float* X, const float* w, const int64_t* idx, int64_t B, int d, int d_pad, int k, float* xt, float* wt,
+                float* mx, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st) {
+  const size_t sm1 = (size_t)128 * (d_pad + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_gather128_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = (int)((B + 127) / 128);
+  k_gather128_pack<<<(unsigned)(ntiles + k), 256, sm1, st>>>(X, w, idx, B, d_pad, xt, wt, mx, k, params, diag, d, pwt, nrm);
+  return (int)cudaGetLastError();
+}
+
 size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
 size_t stash_floats(int64_t B, int k) { return (size_t)((B + 127) / 128) * (size_t)k * ST_TILE; }
 
@@ -22,7 +33,6 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
             float* stash, cudaStream_t st) {
   const TcPack TL(d);
-  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);

@@ -212,11 +212,11 @@ struct TcPack {
 };
 
 // one CTA per net: flat parameters -> TcPack image in global memory (hi / lo split done here, once per step)
-__global__ void k_pack_tc(const float* __restrict__ params, const float* __restrict__ diag_coeff, int d,
-                          float* __restrict__ pwt, float* __restrict__ nrm) {
+__device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ params, const float* __restrict__ diag_coeff, int d,
+                                             float* __restrict__ pwt, float* __restrict__ nrm) {
   constexpr int H = TH;
   const TcPack L(d);
-  const int net = blockIdx.x, K1 = L.K1();
+  const int K1 = L.K1();
   const float* p = params + (size_t)net * flat_net_size<H>(d);
   float* o = pwt + (size_t)net * L.total();
   const float* W1 = p;
@@ -267,6 +267,20 @@ __global__ void k_pack_tc(const float* __restrict__ params, const float* __restr
     for (int i = 0; i < H; i++) m = fmaxf(m, sn[threadIdx.x][i]);
     nrm[kNrmPerNet * net + threadIdx.x] = m;
   }
+}
+__global__ void k_pack_tc(const float* __restrict__ params, const float* __restrict__ diag_coeff, int d,
+                          float* __restrict__ pwt, float* __restrict__ nrm) {
+  pack_tc_body(blockIdx.x, params, diag_coeff, d, pwt, nrm);
+}
+// The minibatch gather and the weight packing are independent: one launch, CTAs [0, k) pack one net each (scheduled first:
+// the packing is latency-bound - 15 us on its own - and hides behind the gather), CTAs [k, k + ntiles) gather a tile each.
+__global__ void __launch_bounds__(256)
+k_gather128_pack(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B, int d_pad,
+                 float* __restrict__ xt, float* __restrict__ wt, float* __restrict__ mx, int knets,
+                 const float* __restrict__ params, const float* __restrict__ diag_coeff, int d, float* __restrict__ pwt,
+                 float* __restrict__ nrm) {
+  if ((int)blockIdx.x < knets) { pack_tc_body((int)blockIdx.x, params, diag_coeff, d, pwt, nrm); return; }
+  gather128_body<0>(X, w, idx, B, d_pad, xt, wt, mx, (int64_t)blockIdx.x - knets);
 }
 
 // issue one 3xTF32 mat-vec chain: D[128 x 32] = A[128 x 8 KS] * B, small terms first (the accumulator truncates).
