@@ -29,7 +29,9 @@ namespace epde {
 namespace tc {
 
 constexpr int P2G = 2;                          // groups per CTA (long-lived per-sample state stays in registers)
-constexpr int P2THREADS = 128 * P2G;
+constexpr int P2THREADS = 128 * P2G + 128;      // + a third warpgroup: one of its warps does nothing but issue the rounds' MMAs, the
+                                                // other three only donate their registers (setmaxnreg works per warpgroup)
+constexpr int P2CTHREADS = 128 * P2G;           // compute threads
 constexpr int P2F = 1;                          // tiles accumulated in TMEM between flushes; must stay 1 while some staging scales are per-tile
 // staging images are MN-major, no swizzle: element (feature f, sample n) of an image at
 //   (f / 8) * SG_SMN + (n / 8) * 128 + (n % 8) * 16 + (f % 8) * 2   bytes,
@@ -91,6 +93,29 @@ __device__ __forceinline__ void issue_round(uint32_t d_t, uint32_t sg_base, uint
 #pragma unroll
   for (int ks = 0; ks < 8; ks++) mma_ss16(d_t, mh + 16 * ks, nh + 16 * ks, idesc, 1u);
 }
+// the same with every operand a run-time value (one copy of the code serves both groups and the three round types: the
+// issuing warp lives on 40 registers)
+__device__ __forceinline__ void issue_round_rt(uint32_t d_t, uint32_t sg_base, uint32_t idesc) {
+  const uint64_t mh = kdesc(sg_base, 128, SG_SMN), ml = kdesc(sg_base + SG_IMG, 128, SG_SMN);
+  const uint64_t nh = kdesc(sg_base + 2 * SG_IMG, 128, SG_SMN), nl = kdesc(sg_base + 3 * SG_IMG, 128, SG_SMN);
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    mma_ss16(d_t, ml + 16 * ks, nh + 16 * ks, idesc, ks ? 1u : 0u);
+    mma_ss16(d_t, mh + 16 * ks, nl + 16 * ks, idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) mma_ss16(d_t, mh + 16 * ks, nh + 16 * ks, idesc, 1u);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 __device__ __forceinline__ void tm_ld8(uint32_t t, float* r) {
   uint32_t v[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -119,10 +144,10 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   float* sw = reinterpret_cast<float*>(tsm + P2G * SG_BYTES);       // packed weights
   float* acc = reinterpret_cast<float*>(sg);                        // per-CTA gradient image (GradLayout): built at the END in the (then idle) staging buffers
   float* imgs = sw + L.total();                                     // group-private gradient images
-  uint64_t* bars = reinterpret_cast<uint64_t*>(imgs + P2G * IMT);   // [P2G] mat-vec, [P2G] rounds
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2 * P2G);     // [0] tmem base
+  uint64_t* bars = reinterpret_cast<uint64_t*>(imgs + P2G * IMT);   // [P2G] mat-vec done, [P2G] round done, [P2G] mat-vec requests, [P2G] round requests
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4 * P2G);     // [0] tmem base
   float* scs = reinterpret_cast<float*>(slot + 4);                  // [16] staging scales, [8] flush factors of this net
-  uint32_t* dynm = reinterpret_cast<uint32_t*>(scs + 32) + (threadIdx.x >> 7) * 32;   // this group's [8 vector types][4 warps] tile maxima (float bits)
+  uint32_t* dynm = reinterpret_cast<uint32_t*>(scs + 32) + ((threadIdx.x >> 7) & 1) * 32;   // this group's [8 vector types][4 warps] tile maxima (float bits)
   const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, wq = warp & 3, lane = tid & 31, net = blockIdx.y;
   const int sn = tid & 127;                                         // sample within the tile = TMEM lane
   {
@@ -134,7 +159,10 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     if (tid >= 32 && tid < 40) scs[16 + tid - 32] = coef->fl[net][tid - 32];
     if (tid == 40) { scs[26] = 1.f / coef->sc[net][1]; scs[27] = 1.f / coef->sc[net][12]; }      // 1 / s(g3), 1 / s(x)
   }
-  if (tid == 0) { for (int i = 0; i < 2 * P2G; i++) mbar_init(bars + i, 1); }
+  if (tid == 0) {
+    for (int i = 0; i < 2 * P2G; i++) mbar_init(bars + i, 1);                   // completed by tcgen05.commit
+    for (int i = 2 * P2G; i < 4 * P2G; i++) mbar_init(bars + i, 128);           // completed by the 128 threads of a group
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -240,22 +268,28 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     fence_after();
     TC_ADD(5);
   };
-#define EPDE_P2_ROUND_ISSUE(ISSUE)                                                                       \
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                         \
-    fence_before(); group_bar(g); TC_ADD(1);                                                             \
-    if (wq == 1) { if (elect_one()) { fence_after(); ISSUE; commit(rbar); } __syncwarp(); }              \
-    pend = true; TC_ADD(8);
+  uint64_t* rreq = bars + 3 * P2G + (g & 1);
 
-#define EPDE_P2_ISSUE(ISSUE)                                                                         \
+  // Mat-vecs (nine MMAs, latency-critical) are issued by the group's own warp 0 right after the group barrier.  A round's
+  // 24 MMAs block their issuing thread for ~700 cycles (the MMA queue is 4 deep): issued by a compute warp, that warp
+  // arrives late at the next group barrier and the other three wait for it.  So a compute thread only publishes "my part
+  // of the round's operands is in place" on the group's request barrier (128 arrivals) and a NINTH warp, which has
+  // nothing else to do, issues the round and commits it to the group's round barrier.
+#define EPDE_P2_ROUND_REQ()                                                                              \
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                         \
+    fence_before(); mbar_arrive(rreq); pend = true; TC_ADD(8);
+#define EPDE_P2_MV_REQ(m)                                                                            \
     TC_ADD(0); fence_before(); group_bar(g); TC_ADD(1);                                              \
-    if (wq == 0) { if (elect_one()) { fence_after(); ISSUE; commit(bar); } __syncwarp(); } TC_ADD(2);
-#define EPDE_P2_WAIT() mbar_wait(bar, ph); ph ^= 1; fence_after(); TC_ADD(3);
+    if (wq == 0) { if (elect_one()) { fence_after(); EPDE_P2_MV(m); commit(bar); } __syncwarp(); } TC_ADD(2);
 #define EPDE_P2_MV(m) issue_matvec<3>(tm + dcol, tm + ahi, tm + alo, kdesc(sbase + L.mat(m, 0) * 4, 128, TKH * 32), \
                                       kdesc(sbase + L.mat(m, 1) * 4, 128, TKH * 32), idesc)
+#define EPDE_P2_WAIT() mbar_wait(bar, ph); ph ^= 1; fence_after(); TC_ADD(3);
 
   const int64_t nt128 = (B + 127) / 128;
   const int64_t tstep = (int64_t)gridDim.x * P2G;
   uint32_t lt = 0;                                   // tiles this group has started
+  if (warp < 4 * P2G) {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");         // 384 x 168 registers at launch = 256 x 232 + 128 x 40
 #pragma unroll 1
   for (int64_t t = (int64_t)blockIdx.x * P2G + g; t < nt128; t += tstep, lt++) {
     const int64_t n = t * 128 + sn;
@@ -275,6 +309,8 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     // the flush hides the DRAM latency of the first half and bounds the registers in flight.
     const float* sp = stash + ((size_t)t * K + net) * ST_TILE + sn;
     float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
+    // (requesting z, a1, g1 one tile ahead - across the loop back-edge - was measured and is SLOWER: 0.81 vs 0.77 ms;
+    //  60 more live registers through the flush)
     stash_ld(sp, 5, z); stash_ld(sp, 0, a1); stash_ld(sp, 4, g1);
     if (t + tstep < nt128) {      // the next tile's stash rows (120 rows of 512 B) towards L2: 480 lines, 4 per thread
       const char* nx = reinterpret_cast<const char*>(stash + ((size_t)(t + tstep) * K + net) * ST_TILE);
@@ -300,7 +336,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     }
     tm_st16(pkB, ze1); tm_st4(pkB + 16, ze1 + 16);      // phi'' term of zbar1: parked until S10 (a1 stays parked in pkA)
     store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(0))
+    EPDE_P2_MV_REQ(0)                                   // W2 ubar1
     EPDE_P2_WAIT()
     // ---- S7: ubar2 -> gbar3 = W3 ubar2;  round 1 is staged while that MMA runs ---------------------------
     tm_ld20(tl + dcol, z);
@@ -313,28 +349,30 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     }
     publish_max(0, ub2);
     store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(1))
+    EPDE_P2_MV_REQ(1)                                   // W3 ubar2
     float fn0;                                          // factor of this tile's g3 x ubar2 block (into fd[0] once the previous tile is flushed)
     {
+      // round 1: the M side (static scales) is staged while the mat-vec runs; its completion also means that every thread
+      // of the group has published its maximum, so the N side (ubar2: per-tile scale) follows the wait
       round_wait();
-      {
-        float iub2;
-        const float s0 = scs[0], s1 = scs[1], s2 = scs[2] * ebar, s3 = scs[3], s4s = dyn_scale(0, iub2), s5 = scs[5];
-        fn0 = scs[26] * iub2;
-        stage_rows<8>(sM, [&](int r) -> float {
-          return r < 20 ? g2[r < 20 ? r : 0]
-               : r < 40 ? fmaf(-a3[(r >= 20 && r < 40) ? r - 20 : 0], a3[(r >= 20 && r < 40) ? r - 20 : 0], 1.f) * sw[L.w4() + ((r >= 20 && r < 40) ? r - 20 : 0)]
-               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
-          [&](int r) -> float { return r < 20 ? s0 : r < 40 ? s1 : s2; });
-        stage_rows<8>(sN, [&](int r) -> float {
-          return r < 20 ? ub1[r < 20 ? r : 0] : r < 40 ? ub2[(r >= 20 && r < 40) ? r - 20 : 0]
-               : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
-          [&](int r) -> float { return r < 20 ? s3 : r < 40 ? s4s : s5; });
-      }
+      const float s0 = scs[0], s1 = scs[1], s2 = scs[2] * ebar, s3 = scs[3], s5 = scs[5];
+      stage_rows<8>(sM, [&](int r) -> float {
+        return r < 20 ? g2[r < 20 ? r : 0]
+             : r < 40 ? fmaf(-a3[(r >= 20 && r < 40) ? r - 20 : 0], a3[(r >= 20 && r < 40) ? r - 20 : 0], 1.f) * sw[L.w4() + ((r >= 20 && r < 40) ? r - 20 : 0)]
+             : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
+        [&](int r) -> float { return r < 20 ? s0 : r < 40 ? s1 : s2; });
       TC_ADD(7);
-      EPDE_P2_ROUND_ISSUE(issue_round<64>(tm + D1 + dlane, sgb, window_start ? 0u : 1u))
+      EPDE_P2_WAIT()
+      float iub2;
+      const float s4s = dyn_scale(0, iub2);
+      fn0 = scs[26] * iub2;
+      stage_rows<8>(sN, [&](int r) -> float {
+        return r < 20 ? ub1[r < 20 ? r : 0] : r < 40 ? ub2[(r >= 20 && r < 40) ? r - 20 : 0]
+             : r < 60 ? g1[(r >= 40 && r < 60) ? r - 40 : 0] : 0.f; },
+        [&](int r) -> float { return r < 20 ? s3 : r < 40 ? s4s : s5; });
+      TC_ADD(7);
+      EPDE_P2_ROUND_REQ()
     }
-    EPDE_P2_WAIT()
     // ---- S8: zbar3, s4 -> W3^T zbar3 -------------------------------------------------------------------
     tm_ld20(tl + dcol, z);
     float zb3[H], s4[H];
@@ -346,7 +384,7 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
       v[i] = zb3[i];
     }
     store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(3))
+    EPDE_P2_MV_REQ(3)                                   // W3^T zbar3
     EPDE_P2_WAIT()
     // ---- S9: zbar2 -> W2^T zbar2;  round 2 is staged while that MMA runs ----------------------------------
     tm_ld16(pkA, a1); tm_ld4(pkA + 16, a1 + 16);
@@ -356,27 +394,28 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     for (int i = 0; i < H; i++) { zb2[i] = fmaf(fmaf(-a2[i], a2[i], 1.f), z[i], ze2[i]); v[i] = zb2[i]; }
     publish_max(1, zb2); publish_max(2, zb3); publish_max(3, s4);
     store_vec24(tl + ahi, tl + alo, v);
-    EPDE_P2_ISSUE(EPDE_P2_MV(2))
+    EPDE_P2_MV_REQ(2)                                   // W2^T zbar2
     float fn1, fn2, fn3;
     {
+      // round 2: the N side (a1 | 1 | a2 | 1, static scale) first, the M side (per-tile scales) after the mat-vec wait
       round_wait();
-      {
-        float i6, i7, i8;
-        const float s6 = dyn_scale(1, i6), s7 = dyn_scale(2, i7), s8 = dyn_scale(3, i8), s9 = scs[9], sa = scs[10];
-        fn1 = i6 * (1.f / 16384.f); fn2 = i7 * (1.f / 16384.f); fn3 = i8 * (1.f / 16384.f);
-        stage_rows<8>(sM, [&](int r) -> float {
-          return r < 20 ? zb2[r < 20 ? r : 0] : r < 40 ? zb3[(r >= 20 && r < 40) ? r - 20 : 0]
-               : r < 60 ? s4[(r >= 40 && r < 60) ? r - 40 : 0] : r == 60 ? ybar : 0.f; },
-          [&](int r) -> float { return r < 20 ? s6 : r < 40 ? s7 : r < 60 ? s8 : s9; });
-        stage_rows<6>(sN, [&](int r) -> float {          // a1 | 1 | a2 | 1, rows 42..47 zero
-          return r < 20 ? a1[r < 20 ? r : 0] : r == 20 ? 1.f : r < 41 ? a2[(r >= 21 && r < 41) ? r - 21 : 0]
-               : r == 41 ? 1.f : 0.f; },
-          [&](int) -> float { return sa; });
-      }
+      const float s9 = scs[9], sa = scs[10];
+      stage_rows<6>(sN, [&](int r) -> float {          // rows 42..47 zero
+        return r < 20 ? a1[r < 20 ? r : 0] : r == 20 ? 1.f : r < 41 ? a2[(r >= 21 && r < 41) ? r - 21 : 0]
+             : r == 41 ? 1.f : 0.f; },
+        [&](int) -> float { return sa; });
       TC_ADD(7);
-      EPDE_P2_ROUND_ISSUE(issue_round<48>(tm + D2 + dlane, sgb, window_start ? 0u : 1u))
+      EPDE_P2_WAIT()
+      float i6, i7, i8;
+      const float s6 = dyn_scale(1, i6), s7 = dyn_scale(2, i7), s8 = dyn_scale(3, i8);
+      fn1 = i6 * (1.f / 16384.f); fn2 = i7 * (1.f / 16384.f); fn3 = i8 * (1.f / 16384.f);
+      stage_rows<8>(sM, [&](int r) -> float {
+        return r < 20 ? zb2[r < 20 ? r : 0] : r < 40 ? zb3[(r >= 20 && r < 40) ? r - 20 : 0]
+             : r < 60 ? s4[(r >= 40 && r < 60) ? r - 40 : 0] : r == 60 ? ybar : 0.f; },
+        [&](int r) -> float { return r < 20 ? s6 : r < 40 ? s7 : r < 60 ? s8 : s9; });
+      TC_ADD(7);
+      EPDE_P2_ROUND_REQ()
     }
-    EPDE_P2_WAIT()
     // ---- S10: zbar1;  round 3 ----------------------------------------------------------------------------
     tm_ld16(pkB, ze1); tm_ld4(pkB + 16, ze1 + 16);
     tm_ld20(tl + dcol, z);
@@ -387,45 +426,75 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
       for (int i = 0; i < H; i++) z[i] = fmaf(fmaf(-a1[i], a1[i], 1.f), z[i], ze1[i]);      // zbar1
       publish_max(4, z);
-      fence_before(); group_bar(g);
       round_wait();
-      float fn4;
-      {
-        float i11;
-        const float s11 = dyn_scale(4, i11), s12 = scs[12];
-        fn4 = i11 * scs[27];
-        stage_rows<3>(sM, [&](int r) -> float { return r < 20 ? z[r < 20 ? r : 0] : 0.f; },   // rows 20..23 zero (24..63: stale finite values, ignored)
-                      [&](int) -> float { return s11; });
-        stage_rows<KSC>(sN, [&](int r) -> float { return xv[r < 64 ? r : 0]; }, [&](int) -> float { return s12; });      // x | 1 | 0...
-      }
+      const float s12 = scs[12];
+      stage_rows<KSC>(sN, [&](int r) -> float { return xv[r < 64 ? r : 0]; }, [&](int) -> float { return s12; });      // x | 1 | 0...
       TC_ADD(7);
-      EPDE_P2_ROUND_ISSUE(issue_round<K1>(tm + D3 + dlane, sgb, window_start ? 0u : 1u))
-      fd[4] = fn4;
+      fence_before(); group_bar(g);                     // every warp's maximum of zbar1 is published
+      TC_ADD(1);
+      float i11;
+      const float s11 = dyn_scale(4, i11);
+      fd[4] = i11 * scs[27];
+      stage_rows<3>(sM, [&](int r) -> float { return r < 20 ? z[r < 20 ? r : 0] : 0.f; },   // rows 20..23 zero (24..63: stale finite values, ignored)
+                    [&](int) -> float { return s11; });
+      TC_ADD(7);
+      EPDE_P2_ROUND_REQ()
     }
     fd[0] = fn0; fd[1] = fn1; fd[2] = fn2; fd[3] = fn3;       // this tile's accumulators are flushed at the start of the next one
   }
-#undef EPDE_P2_ROUND_ISSUE
-#undef EPDE_P2_ISSUE
-#undef EPDE_P2_WAIT
+#undef EPDE_P2_ROUND_REQ
+#undef EPDE_P2_MV_REQ
 #undef EPDE_P2_MV
-  // ---- all rounds issued: last flush of this group's accumulators ----------------------------------------------
+#undef EPDE_P2_WAIT
+  // ---- all rounds requested: last flush of this group's accumulators -------------------------------------------
   if (lt > 0) { round_wait(); flush1(); flush2(); flush3(); }
+  } else {
+    // ---- the issuing warp: serves the round requests of both groups (fixed order per group: rounds 1, 2, 3 per tile) ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");        // this warpgroup's registers go to the compute warps
+    if (warp == 4 * P2G && elect_one()) {
+      uint32_t rn[P2G], ri[P2G];
+#pragma unroll
+      for (int q = 0; q < P2G; q++) {
+        const int64_t first = (int64_t)blockIdx.x * P2G + q;
+        rn[q] = first < nt128 ? 3u * (uint32_t)((nt128 - 1 - first) / tstep + 1) : 0u;
+        ri[q] = 0u;
+      }
+      uint32_t idle = 0;
+      int q = 0;
+      while (ri[0] < rn[0] || ri[1] < rn[1]) {
+        const uint32_t done = q ? ri[1] : ri[0], want = q ? rn[1] : rn[0];
+        if (done < want && mbar_test(bars + 3 * P2G + q, done & 1u)) {
+          fence_after();
+          const uint32_t ty = done % 3u;
+          const uint32_t dcolq = ty == 0 ? D1 : (ty == 1 ? D2 : D3);
+          const uint32_t idq = ty == 0 ? idesc_f16(64, 64) : (ty == 1 ? idesc_f16(64, 48) : idesc_f16(64, K1));
+          issue_round_rt(tm + dcolq + ((uint32_t)(16 * q) << 16), smem_u32(sg) + (uint32_t)q * SG_BYTES, idq);
+          commit(bars + P2G + q);
+          if (q) ri[1]++; else ri[0]++;
+          idle = 0;
+        } else if (++idle > (1u << 26)) __trap();           // a protocol error traps instead of hanging the GPU
+        q ^= 1;
+      }
+    }
+    return;                                               // the epilogue below belongs to the 256 compute threads
+  }
+  auto cbar = [&]() { asm volatile("bar.sync 3, 256;" ::: "memory"); };      // barrier of the compute threads
   fence_before();
-  __syncthreads();
+  cbar();
   fence_after();
   {  // the two group images -> GradLayout image of this CTA (fixed order: group 0 + group 1)
     const float* I0 = imgs; const float* I1 = imgs + IMT;
-    for (int e = tid; e < H * H; e += P2THREADS) {
+    for (int e = tid; e < H * H; e += P2CTHREADS) {
       const int r = e / H, c = e % H;
       acc[G.gW2() + e] = I0[IM_W2 + r * IM_S + c] + I1[IM_W2 + r * IM_S + c];
       acc[G.gW3() + e] = I0[IM_W3 + r * IM_S + c] + I1[IM_W3 + r * IM_S + c];
       acc[G.Gam() + e] = I0[IM_G + r * IM_S + c] + I1[IM_G + r * IM_S + c];
     }
-    for (int e = tid; e < H * d_pad; e += P2THREADS) {
+    for (int e = tid; e < H * d_pad; e += P2CTHREADS) {
       const int r = e / d_pad, c = e % d_pad;
       acc[G.gW1() + e] = (c < d) ? I0[IM_W1 + r * S3 + c] + I1[IM_W1 + r * S3 + c] : 0.f;
     }
-    for (int r = tid; r < H; r += P2THREADS) {
+    for (int r = tid; r < H; r += P2CTHREADS) {
       acc[G.gb1() + r] = I0[IM_W1 + r * S3 + d] + I1[IM_W1 + r * S3 + d];
       acc[G.gb2() + r] = I0[IM_W2 + r * IM_S + 20] + I1[IM_W2 + r * IM_S + 20];
       acc[G.gb3() + r] = I0[IM_W3 + r * IM_S + 20] + I1[IM_W3 + r * IM_S + 20];
@@ -433,9 +502,9 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     }
     if (tid == 0) acc[G.gb4()] = I0[IM_W4 + 20] + I1[IM_W4 + 20];
   }
-  __syncthreads();
+  cbar();
   float* dst = pg + ((size_t)blockIdx.x * gridDim.y + net) * gn;
-  for (int i = tid; i < gn; i += P2THREADS) dst[i] = acc[i];
+  for (int i = tid; i < gn; i += P2CTHREADS) dst[i] = acc[i];
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tm));
 }
 
