@@ -130,8 +130,10 @@ cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, co
   return cudaGetLastError();
 }
 
+struct Deferred { int on, gx, g2; };      // epde_step: phase 1's final reduction is merged into the coefficient launch
+
 int fused_partial(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
-                  const float* params, const float* diag, void* ws, double* sums, cudaStream_t st) {
+                  const float* params, const float* diag, void* ws, double* sums, cudaStream_t st, Deferred* df = nullptr) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   const int impl = fused_impl(D);
@@ -141,16 +143,11 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
     e = cudaMemsetAsync(W.mx, 0, (size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4, st);     // maxima are gathered with atomicMax
     if (e != cudaSuccess) return (int)e;
   }
-  if (impl == 1) {
-    rc = tc::gather_pack(X, w, idx, B, D->d, D->d_pad, D->k, W.xt, W.wt, W.mx, params, diag, W.pwt, W.nrm, st);
-    if (rc) return rc;
-  } else {
-    e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, 0, nullptr);
-    if (e != cudaSuccess) return (int)e;
-  }
+  e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
+  if (e != cudaSuccess) return (int)e;
   if (impl == 1)
     return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
-                       W.mx, W.nrm, W.stash, st);
+                       W.mx, W.nrm, W.stash, st, df ? 1 : 0, df ? &df->gx : nullptr, df ? &df->g2 : nullptr);
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
@@ -170,10 +167,15 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
 
 int fused_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                  const float* params, const float* diag, double beta, double alpha, const EigW& ew,
-                 const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
+                 const double* sums, void* ws, double* out, float* grad, cudaStream_t st, const Deferred* df = nullptr) {
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   const int impl = fused_impl(D);
+  if (impl == 1 && df && df->on) {
+    rc = tc::reduce_coef(W.part, df->gx, W.part2, df->g2, D->k, const_cast<double*>(sums), beta, alpha, ew,
+                         (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef, W.mx, W.nrm, st);
+    if (rc) return rc;
+  } else
   k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef,
                               impl == 1 ? W.mx : nullptr, impl == 1 ? W.nrm : nullptr);
   if (impl == 1) {
@@ -337,6 +339,14 @@ int epde_step(const epde_desc* D, const float* X, const float* w, const int64_t*
   if (!out) return EPDE_ERR_NULL;
   size_t need; epde_workspace_bytes(D, B, &need);
   double* sums = (double*)((char*)ws + need - kSumsTail);
+  if (fused_ok(D) && fused_impl(D) == 1) {       // single rank, tensor-core family: one launch less between the phases
+    if (!h_eig_w || !grad) return EPDE_ERR_NULL;
+    EigW ew; memset(&ew, 0, sizeof(ew));
+    for (int i = 0; i < D->k; i++) ew.v[i] = h_eig_w[i];
+    Deferred df = {1, 0, 0};
+    rc = fused_partial(D, X, w, idx, B, params, diag, ws, sums, (cudaStream_t)stream, &df); if (rc) return rc;
+    return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, (cudaStream_t)stream, &df);
+  }
   rc = epde_step_partial(D, X, w, idx, B, params, diag, ws, ws_bytes, sums, stream); if (rc) return rc;
   return epde_step_finish(D, X, w, idx, B, params, diag, beta, alpha, h_eig_w, sums, ws, ws_bytes, out, grad, stream);
 }

@@ -31,10 +31,9 @@ struct EigW { double v[EPDE_MAX_K]; };
 // (src/pytorch_eigen_solver.py:215-229, 177-189) and the per-sample seed coefficients of the
 // reverse pass (SURVEY.md 8(a) closed form).  One thread (k <= 8); the staging bounds of the tensor-core family: one thread per net.
 template <int DUMMY = 0>
-__global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
-                       double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx = nullptr,
-                       const float* __restrict__ nrm = nullptr) {
-  if (blockIdx.x != 0) return;
+__device__ __forceinline__ void coef_body(const double* sums, int k, double beta, double alpha, const EigW& eigw, int sort,
+                                          double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx,
+                                          const float* __restrict__ nrm) {
   if (threadIdx.x == 0) {
   const double W = sums[0];
   const double* S1 = sums + 1;
@@ -128,6 +127,13 @@ __global__ void k_coef(const double* __restrict__ sums, int k, double beta, doub
         }
       }
   }
+}
+template <int DUMMY = 0>
+__global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
+                       double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx = nullptr,
+                       const float* __restrict__ nrm = nullptr) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  coef_body<DUMMY>(sums, k, beta, alpha, eigw, sort, out, coef, mx, nrm);
 }
 
 

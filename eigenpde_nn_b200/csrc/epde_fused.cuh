@@ -740,14 +740,21 @@ __global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int
   const int gn = G.total();
   const int net = blockIdx.x, S = gridDim.y, sl = blockIdx.y;
   auto red = [&](int e) {
-    double s = 0.0;                              // fixed order; the loads of eight CTAs are in flight together
+    double s = 0.0;                              // fixed order; the loads of sixteen CTAs are in flight together
     int c = 0;
-    for (; c + 8 <= ncta; c += 8) {
-      float v[8];
+    for (; c + 16 <= ncta; c += 16) {
+      float v[16];
 #pragma unroll
-      for (int q = 0; q < 8; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
+      for (int q = 0; q < 16; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
 #pragma unroll
-      for (int q = 0; q < 8; q++) s += (double)v[q];
+      for (int q = 0; q < 16; q++) s += (double)v[q];
+    }
+    for (; c + 4 <= ncta; c += 4) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
+#pragma unroll
+      for (int q = 0; q < 4; q++) s += (double)v[q];
     }
     for (; c < ncta; c++) s += (double)__ldg(pg + ((size_t)c * K + net) * gn + e);
     return s;

@@ -15,24 +15,16 @@ extern "C" int epde_debug_tc_cycles(unsigned long long* h16, int reset) {
 namespace epde {
 namespace tc {
 
-// minibatch gather (128-sample tiles) + weight packing in one launch
-int gather_pack(const float* X, const float* w, const int64_t* idx, int64_t B, int d, int d_pad, int k, float* xt, float* wt,
-                float* mx, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st) {
-  const size_t sm1 = (size_t)128 * (d_pad + 1) * 4;
-  cudaError_t e = cudaFuncSetAttribute(k_gather128_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-  if (e != cudaSuccess) return (int)e;
-  const int ntiles = (int)((B + 127) / 128);
-  k_gather128_pack<<<(unsigned)(ntiles + k), 256, sm1, st>>>(X, w, idx, B, d_pad, xt, wt, mx, k, params, diag, d, pwt, nrm);
-  return (int)cudaGetLastError();
-}
-
 size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
 size_t stash_floats(int64_t B, int k) { return (size_t)((B + 127) / 128) * (size_t)k * ST_TILE; }
 
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
-            float* stash, cudaStream_t st) {
+            float* stash, cudaStream_t st, int defer_reduce, int* gx_out, int* g2_out) {
   const TcPack TL(d);
+  // (packing inside the gather's launch - extra CTAs scheduled first - was measured: the merged kernel takes 141 us against
+  //  115 + 15 us for the two launches; kept separate)
+  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
@@ -64,7 +56,15 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
     case 5: k_sums_y<5><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
     default: k_sums_y<6><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
   }
-  k_reduce_tc<<<1, 1024, 0, st>>>(part, gx, part2, g2, k, sums);      // one warp per sum (34 sums for k = 6)
+  if (gx_out) *gx_out = gx;
+  if (g2_out) *g2_out = g2;
+  if (!defer_reduce) k_reduce_tc<<<1, 1024, 0, st>>>(part, gx, part2, g2, k, sums);      // one warp per sum (34 sums for k = 6)
+  return (int)cudaGetLastError();
+}
+
+int reduce_coef(const double* part, int gx, const double* part2, int g2, int k, double* sums, double beta, double alpha,
+                const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st) {
+  k_reduce_coef_tc<<<1, 1024, 0, st>>>(part, gx, part2, g2, k, sums, beta, alpha, ew, sort, out, coef, mx, nrm);
   return (int)cudaGetLastError();
 }
 

@@ -227,10 +227,16 @@ __device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ 
   const float* b3 = W3 + H * H;
   const float* W4 = b3 + H;
   const float* b4 = W4 + H;
+  // W1 and diag(c) through shared memory: K = W1 diag(c) W1^T reads every element of W1 twenty times (d <= 63 in this family)
+  __shared__ float sW1[TH * 64];
+  __shared__ float sdg[64];
+  for (int e = threadIdx.x; e < H * d; e += blockDim.x) sW1[e] = W1[e];
+  for (int e = threadIdx.x; e < d; e += blockDim.x) sdg[e] = diag_coeff[e];
+  __syncthreads();
   for (int e = threadIdx.x; e < TN * K1; e += blockDim.x) {
     const int n = e / K1, k = e % K1;
     float v = 0.f;
-    if (n < H) v = (k < d) ? W1[n * d + k] : (k == d ? b1[n] : 0.f);
+    if (n < H) v = (k < d) ? sW1[n * d + k] : (k == d ? b1[n] : 0.f);
     float hi, lo; split_tf32(v, hi, lo);
     o[L.W1f(0) + kmaj_off(n, k, K1)] = hi; o[L.W1f(1) + kmaj_off(n, k, K1)] = lo;
   }
@@ -244,7 +250,7 @@ __device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ 
       else if (m == 3) v = (k < H) ? W3[k * H + n] : 0.f;
       else if (k < H) {
         double s = 0.0;
-        for (int j = 0; j < d; j++) s += (double)diag_coeff[j] * (double)W1[n * d + j] * (double)W1[k * d + j];
+        for (int j = 0; j < d; j++) s += (double)sdg[j] * (double)sW1[n * d + j] * (double)sW1[k * d + j];
         v = (float)s;
       }
     }
@@ -272,17 +278,6 @@ __global__ void k_pack_tc(const float* __restrict__ params, const float* __restr
                           float* __restrict__ pwt, float* __restrict__ nrm) {
   pack_tc_body(blockIdx.x, params, diag_coeff, d, pwt, nrm);
 }
-// The minibatch gather and the weight packing are independent: one launch, CTAs [0, k) pack one net each (scheduled first:
-// the packing is latency-bound - 15 us on its own - and hides behind the gather), CTAs [k, k + ntiles) gather a tile each.
-__global__ void __launch_bounds__(256)
-k_gather128_pack(const float* __restrict__ X, const float* __restrict__ w, const int64_t* __restrict__ idx, int64_t B, int d_pad,
-                 float* __restrict__ xt, float* __restrict__ wt, float* __restrict__ mx, int knets,
-                 const float* __restrict__ params, const float* __restrict__ diag_coeff, int d, float* __restrict__ pwt,
-                 float* __restrict__ nrm) {
-  if ((int)blockIdx.x < knets) { pack_tc_body((int)blockIdx.x, params, diag_coeff, d, pwt, nrm); return; }
-  gather128_body<0>(X, w, idx, B, d_pad, xt, wt, mx, (int64_t)blockIdx.x - knets);
-}
-
 // issue one 3xTF32 mat-vec chain: D[128 x 32] = A[128 x 8 KS] * B, small terms first (the accumulator truncates).
 // Straight-line code with compile-time offsets: every operand of UTCHMMA lives in a uniform register, and
 // anything computed per MMA on the uniform datapath costs far more than the MMA itself (18 cycles).
@@ -566,9 +561,8 @@ k_sums_y(const float* __restrict__ wt, const float* __restrict__ ybuf, int64_t B
 
 // sums = [W, S1(k), E(k), S2(k(k+1)/2)] from the two partial arrays; one warp per sum, fixed (lane-strided, then
 // shuffle-tree) order
-__global__ void __launch_bounds__(1024)
-k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K,
-            double* __restrict__ sums) {
+__device__ __forceinline__ void reduce_tc_body(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2,
+                                               int K, double* sums) {
   const int lane = threadIdx.x & 31;
   const int ns2 = 1 + K * (K + 1) / 2, ns = 1 + 2 * K + K * (K + 1) / 2;       // 34 sums for k = 6
   for (int s = threadIdx.x >> 5; s < ns; s += blockDim.x >> 5) {
@@ -583,6 +577,21 @@ k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ 
     v = warp_sum(v);
     if (lane == 0) sums[s] = v;
   }
+}
+__global__ void __launch_bounds__(1024)
+k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K,
+            double* __restrict__ sums) {
+  reduce_tc_body(part, gx, part2, g2, K, sums);
+}
+// single-rank step: the reduction of the partials and the coefficient kernel in one launch (no exchange in between)
+__global__ void __launch_bounds__(1024)
+k_reduce_coef_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K, double* sums,
+                 double beta, double alpha, EigW eigw, int sort, double* __restrict__ out, Coef* __restrict__ coef,
+                 const float* __restrict__ mx, const float* __restrict__ nrm) {
+  reduce_tc_body(part, gx, part2, g2, K, sums);
+  __threadfence_block();
+  __syncthreads();
+  if (threadIdx.x < 32) coef_body<0>(sums, K, beta, alpha, eigw, sort, out, coef, mx, nrm);
 }
 
 }  // namespace tc
