@@ -439,8 +439,10 @@ def main():
         "e2e": {"value": total / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": 4 * eng.n_params,
                 "d2h_bytes_per_step": 8 * eng.out.numel() + 4 * eng.n_params,
                 "minibatch": "fresh draw every step from the reference's MT19937 stream, generated on the device inside the "
-                             "timed region (epde_minibatch_indices_device, %d draws per rank and step: every rank advances the "
-                             "global stream), one step ahead on a second stream; no index upload" % (world * B)},
+                             "timed region (epde_minibatch_indices_device), one step ahead on a second stream; no index upload; "
+                             + ("every rank jumps ahead to its slice of the %d-draw global batch (x^J mod the characteristic "
+                                "polynomial, epde_mt_jump_device) and generates only its own %d draws" % (world * B, B)
+                                if world > 1 else "%d draws per step" % B)},
         # per step: memset, k_gather128, k_pack_tc, k_pass1_tc, k_sums_y, k_reduce_tc, k_coef, k_pass2_tc, k_fin2 (+ 2 exchange kernels)
         "gpu_launches": (8 + (2 if world > 1 else 0)) * args.steps, "clocks": clocks,
     }

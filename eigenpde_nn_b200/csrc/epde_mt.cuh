@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // state[0..623] = mt, state[624] = pos (0..624).  Consumes W = 2 * B words (W < 2^31) starting at position pos of the
 // current block and writes them (untempered) to raw[0..W).  One CTA of MT_THREADS threads; 32-bit index arithmetic and
 // warp-uniform branches only (the CTA is issue-bound: 20 warps on one SM).
-__global__ void __launch_bounds__(MT_THREADS, 1)
+static __global__ void __launch_bounds__(MT_THREADS, 1)
 k_mt_generate(uint32_t* __restrict__ state, int W, uint32_t* __restrict__ raw) {
   __shared__ uint32_t buf[MT_N + MT_STEP * MT_CHUNK];
   const int tid = threadIdx.x;
@@ -81,7 +81,7 @@ k_mt_generate(uint32_t* __restrict__ state, int W, uint32_t* __restrict__ raw) {
 }
 
 // idx[i] = min(floor(u * K), K - 1) for draws out_lo + i, i < out_n, from the raw words of k_mt_generate
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_mt_to_idx(const uint32_t* __restrict__ raw, int64_t K, int64_t out_lo, int64_t out_n, int64_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= out_n) return;

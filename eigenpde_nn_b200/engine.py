@@ -236,6 +236,9 @@ class DeviceMinibatch:
         self._raw = None
         self._py_meta = None
         self.seeded = False
+        # jump-ahead (sharded draws): polynomials x^J mod phi per jump distance, scratch states, the 20 560-word window
+        self._polys = {}
+        self._jump = None
 
     def seed_from_python(self):
         import random
@@ -254,14 +257,52 @@ class DeviceMinibatch:
         version, gauss = self._py_meta
         random.setstate((version, tuple(int(v) for v in st), gauss))
 
+    def _poly(self, J):
+        """x^J mod (characteristic polynomial of MT19937) on the device; computed once per jump distance on the host."""
+        t = self._polys.get(J)
+        if t is None:
+            host = np.zeros(624, dtype=np.uint32)
+            _lib.check(self.lib.epde_mt_jump_poly(C.c_int64(J), host.ctypes.data_as(C.c_void_p)), "epde_mt_jump_poly")
+            t = torch.from_numpy(host.view(np.int32)).to(self.device)
+            self._polys[J] = t
+        return t
+
+    def _draw_slice(self, B_total, out, lo, n):
+        """Sharded draw: jump to this rank's slice (2 * lo words) and to the next step (2 * B_total words) from one window of
+        the base state, then generate only the 2 * n words of the slice (csrc/epde_mt_jump.cu)."""
+        if self._jump is None:
+            dev = self.device
+            self._jump = dict(slice=torch.zeros(625, dtype=torch.int32, device=dev), nxt=torch.zeros(625, dtype=torch.int32, device=dev),
+                              win=torch.empty(20560, dtype=torch.int32, device=dev), key=None, polys=None)
+        J = self._jump
+        if J["key"] != (B_total, lo):
+            J["polys"] = torch.cat([self._poly(2 * lo), self._poly(2 * B_total)]).contiguous()
+            J["key"] = (B_total, lo)
+            J["outs"] = (C.c_void_p * 2)(J["slice"].data_ptr(), J["nxt"].data_ptr())
+        if self._raw is None or self._raw.numel() < 2 * n:
+            self._raw = torch.empty(max(2 * n, 2), dtype=torch.int32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.epde_mt_jump_device(_ptr(self.state), _ptr(J["polys"]), 2, J["outs"], _ptr(J["win"]), st),
+                   "epde_mt_jump_device")
+        if n > 0:
+            _lib.check(self.lib.epde_minibatch_indices_device(_ptr(J["slice"]), C.c_int64(self.K), C.c_int64(n), C.c_int64(0),
+                                                              C.c_int64(n), _ptr(self._raw), _ptr(out), st),
+                       "epde_minibatch_indices_device")
+        self.state.copy_(J["nxt"])                  # same address every step: the draw can sit inside a replayed CUDA graph
+        return out
+
     def draw(self, B_total, out=None, lo=0, n=None):
-        """Enqueue B_total draws on the current stream; the indices of draws [lo, lo + n) go to `out` (int64, device)."""
+        """Enqueue B_total draws on the current stream; the indices of draws [lo, lo + n) go to `out` (int64, device).
+        A proper slice (a rank of a sharded step) is reached by jump-ahead: only its own 2 * n words are generated."""
         assert self.seeded, "call seed_from_python() first"
         n = B_total - lo if n is None else n
         if out is None:
             out = torch.empty(n, dtype=torch.int64, device=self.device)
         if B_total == 0:
             return out
+        import os
+        if (lo != 0 or n != B_total) and os.environ.get("EPDE_MT_JUMP", "1") != "0":
+            return self._draw_slice(B_total, out, lo, n)
         if self._raw is None or self._raw.numel() < 2 * B_total:
             self._raw = torch.empty(2 * B_total, dtype=torch.int32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -177,6 +177,21 @@ int epde_minibatch_indices(uint32_t* h_mt, int32_t* h_pos, int64_t K, int64_t B,
 int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total, int64_t out_lo, int64_t out_n,
                                   uint32_t* d_raw, int64_t* d_idx, void* stream);
 
+/*
+ * Jump-ahead for the sharded stream (csrc/epde_mt_jump.cu).  MT19937 is linear over GF(2): the generator J words ahead is a
+ * fixed XOR-combination, given by g_J(x) = x^J mod (characteristic polynomial), of the next 20 560 words.
+ *   epde_mt_jump_poly: host, g_J as 624 uint32 (about 0.2 s; depends only on J -- compute once per slice offset / batch size).
+ *   epde_mt_jump_device: from the generator d_state_in (625 uint32) produce, for each of the n_polys <= 8 polynomials in
+ *     d_polys (n_polys x 624 uint32, device), the generator advanced by that jump into h_state_out[k] (host array of device
+ *     pointers, 625 uint32 each: the 624-word window at the target position, position word 0 -- the same stream position in
+ *     a different representation than CPython's (block, position) pair).  d_window: scratch of 20 560 uint32.
+ * A rank of a sharded step jumps to its slice (2 * lo words) and to the next step (2 * B words) and generates only its own
+ * draws with epde_minibatch_indices_device.
+ */
+int epde_mt_jump_poly(int64_t J, uint32_t* h_poly624);
+int epde_mt_jump_device(const uint32_t* d_state_in, const uint32_t* d_polys, int32_t n_polys, uint32_t* const* h_state_out,
+                        uint32_t* d_window, void* stream);
+
 /* CPython random.seed(int) -> MT19937 state (init_by_array over the 32-bit words of |seed|);
  * `h_key` holds the little-endian 32-bit words of the absolute seed. */
 int epde_mt_seed(const uint32_t* h_key, int32_t key_len, uint32_t* h_mt, int32_t* h_pos);

@@ -98,6 +98,42 @@ def test_full_size_batches_and_rank_slices():
         assert np.array_equal(mr.draw(4096).cpu().numpy(), want2)         # same global stream position on every rank
 
 
+def test_jump_ahead_slices_equal_the_sequential_stream():
+    """Sharded draws by jump-ahead (x^J mod the characteristic polynomial applied to the next 20 560 words): each rank
+    generates only its slice, consecutive steps chain through the jumped base state, and the stream handed back to Python
+    continues exactly like the sequential one (the jumped state is the 624-word window at the same stream position)."""
+    from eigenpde_nn_b200.parallel import shard_bounds
+    K, B, world, steps = 4_194_304, 300_007, 8, 3
+    random.seed(1729)
+    for _ in range(17):
+        random.random()                                     # start inside a block
+    saved = random.getstate()
+    want = [_host_draw(K, B) for _ in range(steps)]
+    follow = [random.random() for _ in range(4)]
+    for rank in (0, 1, 5, 7):
+        random.setstate(saved)
+        mb = _mb(K).seed_from_python()
+        lo, hi = shard_bounds(B, world, rank)
+        for s in range(steps):
+            got = mb.draw(B, lo=lo, n=hi - lo).cpu().numpy()
+            assert np.array_equal(got, want[s][lo:hi]), (rank, s)
+        mb.sync_to_python()
+        assert [random.random() for _ in range(4)] == follow, rank
+
+
+def test_jump_polynomial_identity_and_small_jumps():
+    """x^0 = 1 (the state itself), and a slice that starts at 0 but is shorter than the batch."""
+    K, B = 1000, 5000
+    random.seed(5)
+    saved = random.getstate()
+    want = _host_draw(K, B)
+    want2 = _host_draw(K, B)
+    random.setstate(saved)
+    mb = _mb(K).seed_from_python()
+    assert np.array_equal(mb.draw(B, lo=0, n=1234).cpu().numpy(), want[:1234])
+    assert np.array_equal(mb.draw(B, lo=4000, n=1000).cpu().numpy(), want2[4000:])
+
+
 def test_empty_and_tiny_draws():
     random.seed(3)
     saved = random.getstate()
