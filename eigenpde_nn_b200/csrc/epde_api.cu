@@ -120,8 +120,10 @@ cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, co
     const size_t sm1 = (size_t)128 * (D->d_pad + 1) * 4;
     cudaError_t e1 = cudaFuncSetAttribute(k_gather128<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     if (e1 != cudaSuccess) return e1;
-    k_gather128<0><<<(unsigned)((B + 127) / 128), 256, sm1, st>>>(X, w, idx, B, D->d_pad, xt, wt, mx);
-    return cudaGetLastError();
+    // behind k_pack_tc, which it does not depend on: PDL lets the two run side by side (the gather waits for the packing
+    // only at its very end, so that "gather complete" implies "packing complete" for phase 1)
+    e1 = launch_pdl(k_gather128<0>, dim3((unsigned)((B + 127) / 128)), dim3(256), sm1, st, X, w, idx, B, D->d_pad, xt, wt, mx);
+    return e1 != cudaSuccess ? e1 : cudaGetLastError();
   }
   const size_t smem = (size_t)GT * (D->d_pad + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(k_gather<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -142,6 +144,8 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   else {
     e = cudaMemsetAsync(W.mx, 0, (size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4, st);     // maxima are gathered with atomicMax
     if (e != cudaSuccess) return (int)e;
+    rc = tc::pack(D->d, D->k, params, diag, W.pwt, W.nrm, st);
+    if (rc) return rc;
   }
   e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
   if (e != cudaSuccess) return (int)e;
@@ -182,9 +186,9 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
     int gx = 0;
     rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
     if (rc) return rc;
-    const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
-    k_fin2<kFusedH><<<dim3(D->k, 24), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
-    return (int)cudaGetLastError();
+    cudaError_t e2 = launch_pdl(k_fin2<kFusedH>, dim3(D->k, fin2_items<kFusedH>(D->d)), dim3(1024), 0, st, (const float*)W.pg, gx,
+                                D->k, D->d, D->d_pad, params, diag, grad);
+    return (int)(e2 != cudaSuccess ? e2 : cudaGetLastError());
   }
   const int64_t ntiles = (B + P2_T - 1) / P2_T;
   int gx = nsm / D->k; if (gx < 1) gx = 1;
@@ -195,8 +199,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
                                                               W.coef, W.pg);
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
-  const size_t sm2 = (size_t)kFusedH * kFusedH * 8;
-  k_fin2<kFusedH><<<dim3(D->k, 8), 256, sm2, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+  k_fin2<kFusedH><<<dim3(D->k, fin2_items<kFusedH>(D->d)), 1024, 0, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
   return (int)cudaGetLastError();
 }
 

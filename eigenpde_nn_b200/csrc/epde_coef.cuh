@@ -1,5 +1,6 @@
 // Batch-global coefficient kernel shared by the fused and the generic kernel families.
 #pragma once
+#include "epde_common.cuh"
 #include <cuda_runtime.h>
 #include "../../include/eigenpde_b200.h"
 
@@ -42,14 +43,17 @@ __device__ __forceinline__ void coef_body(const double* sums, int k, double beta
   double m[EPDE_MAX_K], var[EPDE_MAX_K], Rq[EPDE_MAX_K], lam[EPDE_MAX_K], wt[EPDE_MAX_K];
   double cov[EPDE_MAX_K][EPDE_MAX_K];
   int cvec[EPDE_MAX_K];
-  for (int i = 0; i < k; i++) m[i] = S1[i] / W;
+  const double iW = 1.0 / W, iWb = 1.0 / (W * beta);      // (fp64 divisions are ~100 cycles each on this single thread)
+  for (int i = 0; i < k; i++) m[i] = S1[i] * iW;
   int t = 0;
   for (int i = 0; i < k; i++)
-    for (int j = 0; j <= i; j++) { cov[i][j] = cov[j][i] = S2[t] / W - m[i] * m[j]; t++; }
+    for (int j = 0; j <= i; j++) { cov[i][j] = cov[j][i] = S2[t] * iW - m[i] * m[j]; t++; }
+  double ivar[EPDE_MAX_K];
   for (int i = 0; i < k; i++) {
     var[i] = cov[i][i];
-    Rq[i] = E[i] / (W * beta);
-    lam[i] = Rq[i] / var[i];
+    ivar[i] = 1.0 / var[i];
+    Rq[i] = E[i] * iWb;
+    lam[i] = Rq[i] * ivar[i];
     cvec[i] = i;
   }
   if (sort) {   // ascending, stable insertion sort (np.argsort order for distinct values)
@@ -76,13 +80,13 @@ __device__ __forceinline__ void coef_body(const double* sums, int k, double beta
   }
   if (coef) {
     for (int i = 0; i < k; i++) {
-      coef->ecoef[i] = (float)(wt[i] / (W * beta * var[i]));
+      coef->ecoef[i] = (float)(wt[i] * iWb * ivar[i]);
       double cmi = 0.0;
       for (int j = 0; j < k; j++) {
-        const double c = (i == j) ? 2.0 * (-wt[i] * Rq[i] / (var[i] * var[i]) + 2.0 * alpha * (var[i] - 1.0))
+        const double c = (i == j) ? 2.0 * (-wt[i] * Rq[i] * ivar[i] * ivar[i] + 2.0 * alpha * (var[i] - 1.0))
                                   : 2.0 * alpha * cov[i][j];
-        coef->Cw[i][j] = (float)(c / W);
-        cmi += c / W * m[j];
+        coef->Cw[i][j] = (float)(c * iW);
+        cmi += c * iW * m[j];
       }
       coef->cm[i] = (float)cmi;
     }
@@ -132,6 +136,7 @@ template <int DUMMY = 0>
 __global__ void k_coef(const double* __restrict__ sums, int k, double beta, double alpha, EigW eigw, int sort,
                        double* __restrict__ out, Coef* __restrict__ coef, const float* __restrict__ mx = nullptr,
                        const float* __restrict__ nrm = nullptr) {
+  pdl_trigger();                     // phase 2's CTAs may set up shared / tensor memory meanwhile (they wait before reading coef)
   if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   coef_body<DUMMY>(sums, k, beta, alpha, eigw, sort, out, coef, mx, nrm);
 }

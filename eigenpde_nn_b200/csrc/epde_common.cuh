@@ -92,6 +92,25 @@ __device__ __forceinline__ float2 ldg_early2(const float2* p) {
   return *reinterpret_cast<float2*>(&v);
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// A kernel launched with launch_pdl() may START while its predecessor in the stream is still running - as soon as every
+// CTA of the predecessor has executed pdl_trigger() (or exited) - and must execute pdl_wait() before it touches anything
+// the predecessor writes: pdl_wait() returns when the predecessor grid has completed and its writes are visible.
+// Used where a kernel has a prologue that does not depend on its predecessor (shared-memory / tensor-memory set-up) or
+// is independent of it altogether; the chain stays inside one stream and is capturable into a CUDA graph.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

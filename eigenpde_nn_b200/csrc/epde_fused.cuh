@@ -185,6 +185,7 @@ __device__ __forceinline__ void gather128_body(const float* __restrict__ X, cons
   }
   float* out = xt + (size_t)tile * d_pad * 128 + (t & 127);
   for (int j = (t >> 7); j < d_pad; j += 2) out[(size_t)j * 128] = ts[(t & 127) * ld + j];
+  pdl_wait();      // launched alongside k_pack_tc (PDL): this grid's completion must imply the packing's
 }
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(256)
@@ -726,62 +727,68 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fin2: one CTA per net; fixed-order fp64 reduction over the pass-2 CTAs, then
+// k_fin2: fixed-order fp64 reduction of the per-CTA gradient images of phase 2, plus
 //         dW1 += 2 Gamma W1 diag(c)   (the g1 (x) ubar_0 term, via u0 = W1^T g1)
 // ---------------------------------------------------------------------------------------------
+// grid = (K, S), 1024 threads.  Work items of a net: H "row" items (row o of W1: needs row o of Gamma only - 20 elements
+// instead of the whole matrix every CTA used to reduce - and produces the d elements dW1[o][:]) and chunks of
+// FIN2_CHUNK of the remaining elements; CTA (net, s) takes items s, s + S, ...  (fin2_items(d) CTAs per net = one item
+// each).  One WARP per output element: the lanes stride over the phase-2 CTAs (all loads of an element in flight at
+// once) and a fixed shuffle tree adds the lane sums - the same order in every run.
+constexpr int FIN2_CHUNK = 128;
 template <int H>
-__global__ void k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
-                       const float* __restrict__ params, const float* __restrict__ diag_coeff,
-                       float* __restrict__ grad) {
-  // grid = (K, S): CTA (net, s) produces the flat-gradient elements e = s, s + S, ... of its net.  Every CTA reduces
-  // Gamma (H x H) itself - the dW1 correction needs all of it - and only its own share of the other accumulators.
-  extern __shared__ double sred[];               // [H * H] Gamma
+__host__ __device__ inline int fin2_items(int d) { return H + (flat_net_size<H>(d) - H * d + FIN2_CHUNK - 1) / FIN2_CHUNK; }
+template <int H>
+__global__ void __launch_bounds__(1024)
+k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
+       const float* __restrict__ params, const float* __restrict__ diag_coeff, float* __restrict__ grad) {
+  static_assert(H <= 32, "one lane per Gamma column");
+  __shared__ double sG[H];                       // row o of Gamma
+  pdl_wait();                                    // the tensor-core family launches this kernel programmatically (PDL) behind k_pass2_tc
   const GradLayout<H> G(d_pad);
   const int gn = G.total();
-  const int net = blockIdx.x, S = gridDim.y, sl = blockIdx.y;
-  auto red = [&](int e) {
-    double s = 0.0;                              // fixed order; the loads of sixteen CTAs are in flight together
-    int c = 0;
-    for (; c + 16 <= ncta; c += 16) {
-      float v[16];
-#pragma unroll
-      for (int q = 0; q < 16; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
-#pragma unroll
-      for (int q = 0; q < 16; q++) s += (double)v[q];
-    }
-    for (; c + 4 <= ncta; c += 4) {
-      float v[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) v[q] = __ldg(pg + ((size_t)(c + q) * K + net) * gn + e);
-#pragma unroll
-      for (int q = 0; q < 4; q++) s += (double)v[q];
-    }
-    for (; c < ncta; c++) s += (double)__ldg(pg + ((size_t)c * K + net) * gn + e);
+  const int net = blockIdx.x, S = gridDim.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* base = pg + (size_t)net * gn;
+  auto red = [&](int e) -> double {              // this lane's share of element e: CTAs lane, lane + 32, ...
+    double s = 0.0;
+    for (int c = lane; c < ncta; c += 32) s += (double)__ldg(base + (size_t)c * K * gn + e);
     return s;
   };
-  for (int e = threadIdx.x; e < H * H; e += blockDim.x) sred[e] = red(G.Gam() + e);
-  __syncthreads();
-  const int fn = flat_net_size<H>(d);
+  const int fn = flat_net_size<H>(d), nrest = fn - H * d;
+  const int nitems = fin2_items<H>(d);
   const float* W1 = params + (size_t)net * fn;
   float* g = grad + (size_t)net * fn;
-  for (int e = sl * blockDim.x + threadIdx.x; e < fn; e += S * blockDim.x) {
-    double v;
-    if (e < H * d) {
-      const int o = e / d, j = e % d;
-      double corr = 0.0;
-      for (int b = 0; b < H; b++) corr += sred[o * H + b] * (double)W1[b * d + j];
-      v = red(G.gW1() + o * d_pad + j) + 2.0 * (double)diag_coeff[j] * corr;
+  for (int item = blockIdx.y; item < nitems; item += S) {
+    if (item < H) {
+      const int o = item;
+      __syncthreads();                           // sG is re-used when a CTA takes several items
+      for (int b = warp; b < H; b += nw) {
+        const double v = warp_sum(red(G.Gam() + o * H + b));
+        if (lane == 0) sG[b] = v;
+      }
+      __syncthreads();
+      for (int j = warp; j < d; j += nw) {
+        double v = red(G.gW1() + o * d_pad + j);
+        if (lane < H) v += 2.0 * (double)diag_coeff[j] * sG[lane] * (double)W1[lane * d + j];
+        v = warp_sum(v);
+        if (lane == 0) g[o * d + j] = (float)v;
+      }
     } else {
-      int r = e - H * d;
-      if (r < H) v = red(G.gb1() + r);
-      else if ((r -= H) < H * H) v = red(G.gW2() + r);
-      else if ((r -= H * H) < H) v = red(G.gb2() + r);
-      else if ((r -= H) < H * H) v = red(G.gW3() + r);
-      else if ((r -= H * H) < H) v = red(G.gb3() + r);
-      else if ((r -= H) < H) v = red(G.gw4() + r);
-      else v = red(G.gb4());
+      const int r0 = (item - H) * FIN2_CHUNK, r1 = min(nrest, r0 + FIN2_CHUNK);
+      for (int rr = r0 + warp; rr < r1; rr += nw) {
+        int r = rr, e;
+        if (r < H) e = G.gb1() + r;
+        else if ((r -= H) < H * H) e = G.gW2() + r;
+        else if ((r -= H * H) < H) e = G.gb2() + r;
+        else if ((r -= H) < H * H) e = G.gW3() + r;
+        else if ((r -= H * H) < H) e = G.gb3() + r;
+        else if ((r -= H) < H) e = G.gw4() + r;
+        else e = G.gb4();
+        const double v = warp_sum(red(e));
+        if (lane == 0) g[H * d + rr] = (float)v;
+      }
     }
-    g[e] = (float)v;
   }
 }
 

@@ -13,7 +13,10 @@ namespace tc {
 size_t pack_floats(int d);          // floats of one net's packed weight image
 size_t stash_floats(int64_t B, int k);   // floats of the phase-1 -> phase-2 stash (epde_tc_fused.cuh)
 
-// phase 1: k_pack_tc + k_pass1_tc + k_sums_y + k_reduce_tc -> sums[1 + 2k + k(k+1)/2], ybuf[B][k]
+// weight images of all k nets (k_pack_tc); to be launched before the gather, which then runs alongside it (PDL)
+int pack(int d, int k, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st);
+
+// phase 1 after pack() and the gather: k_pass1_tc + k_sums_y + k_reduce_tc -> sums[1 + 2k + k(k+1)/2], ybuf[B][k]
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
             float* stash, cudaStream_t st, int defer_reduce = 0, int* gx_out = nullptr, int* g2_out = nullptr);

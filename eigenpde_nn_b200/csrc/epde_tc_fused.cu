@@ -18,13 +18,17 @@ namespace tc {
 size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
 size_t stash_floats(int64_t B, int k) { return (size_t)((B + 127) / 128) * (size_t)k * ST_TILE; }
 
+int pack(int d, int k, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st) {
+  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
+  return (int)cudaGetLastError();
+}
+
 int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, const float* diag, const float* xt,
             const float* wt, float* pwt, float* ybuf, double* part, double* part2, double* sums, float* mx, float* nrm,
             float* stash, cudaStream_t st, int defer_reduce, int* gx_out, int* g2_out) {
   const TcPack TL(d);
-  // (packing inside the gather's launch - extra CTAs scheduled first - was measured: the merged kernel takes 141 us against
-  //  115 + 15 us for the two launches; kept separate)
-  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
+  // (the weight images were packed by pack(), launched BEFORE the gather so that the two overlap; packing inside the gather's
+  //  launch - extra CTAs scheduled first - was measured: the merged kernel takes 141 us against 115 + 15 us for two launches)
   const int64_t nt128 = (B + 127) / 128;
   int gx = nsm / k; if (gx < 1) gx = 1;
   if ((int64_t)gx * TG > nt128) gx = (int)((nt128 + TG - 1) / TG);
@@ -47,14 +51,14 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
   }
 #undef EPDE_P1_LAUNCH
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
-  int g2 = (int)((B + 255) / 256); if (g2 > nsm) g2 = nsm;
+  int g2 = (int)((B + SY_THREADS - 1) / SY_THREADS); if (g2 > nsm) g2 = nsm;
   switch (k) {
-    case 1: k_sums_y<1><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
-    case 2: k_sums_y<2><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
-    case 3: k_sums_y<3><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
-    case 4: k_sums_y<4><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
-    case 5: k_sums_y<5><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
-    default: k_sums_y<6><<<g2, 256, 0, st>>>(wt, ybuf, B, part2); break;
+    case 1: k_sums_y<1><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
+    case 2: k_sums_y<2><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
+    case 3: k_sums_y<3><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
+    case 4: k_sums_y<4><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
+    case 5: k_sums_y<5><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
+    default: k_sums_y<6><<<g2, SY_THREADS, 0, st>>>(wt, ybuf, B, part2); break;
   }
   if (gx_out) *gx_out = gx;
   if (g2_out) *g2_out = g2;
@@ -64,8 +68,9 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 
 int reduce_coef(const double* part, int gx, const double* part2, int g2, int k, double* sums, double beta, double alpha,
                 const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st) {
-  k_reduce_coef_tc<<<1, 1024, 0, st>>>(part, gx, part2, g2, k, sums, beta, alpha, ew, sort, out, coef, mx, nrm);
-  return (int)cudaGetLastError();
+  cudaError_t e = launch_pdl(k_reduce_coef_tc, dim3(1), dim3(1024), 0, st, part, gx, part2, g2, k, sums, beta, alpha, ew, sort,
+                             out, coef, mx, nrm);
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,
@@ -81,7 +86,8 @@ int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const f
   do {                                                                                                              \
     e = cudaFuncSetAttribute(k_pass2_tc<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return (int)e;                                                                            \
-    k_pass2_tc<__VA_ARGS__><<<dim3(gx, k), P2THREADS, smem, st>>>(xt, wt, B, d, d_pad, k, pwt, ybuf, coef, stash, pg); \
+    e = launch_pdl(k_pass2_tc<__VA_ARGS__>, dim3(gx, k), dim3(P2THREADS), smem, st, xt, wt, B, d, d_pad, k, pwt, ybuf, coef, stash, pg); \
+    if (e != cudaSuccess) return (int)e;                                                                            \
   } while (0)
   const bool std_pad = d_pad == (d + 3) / 4 * 4;
   if (std_pad && d == 50) EPDE_P2_LAUNCH(7, 50);

@@ -276,6 +276,7 @@ __device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ 
 }
 __global__ void k_pack_tc(const float* __restrict__ params, const float* __restrict__ diag_coeff, int d,
                           float* __restrict__ pwt, float* __restrict__ nrm) {
+  pdl_trigger();                     // the gather that follows is independent of the packing: it runs alongside (PDL)
   pack_tc_body(blockIdx.x, params, diag_coeff, d, pwt, nrm);
 }
 // issue one 3xTF32 mat-vec chain: D[128 x 32] = A[128 x 8 KS] * B, small terms first (the accumulator truncates).
@@ -523,28 +524,37 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 }
 
 // W = sum w and S2[i][j] = sum w y_i y_j from wt / ybuf: one fp64 partial row per CTA, part2[cta][1 + K(K+1)/2]
+// (latency-bound: 1024 threads per CTA and two samples per iteration keep 8x the loads of the first version in flight)
+constexpr int SY_THREADS = 1024;
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SY_THREADS)
 k_sums_y(const float* __restrict__ wt, const float* __restrict__ ybuf, int64_t B, double* __restrict__ part2) {
   constexpr int NS2 = 1 + K * (K + 1) / 2;
+  pdl_trigger();                     // the reduction kernel may take its place (it waits for this grid before reading)
   double acc[NS2];
 #pragma unroll
   for (int s = 0; s < NS2; s++) acc[s] = 0.0;
-  for (int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x; n < B; n += (int64_t)gridDim.x * 256) {
-    const float w = __ldg(wt + n);
-    float y[K];
+  const int64_t stride = (int64_t)gridDim.x * SY_THREADS;
+  for (int64_t n0 = (int64_t)blockIdx.x * SY_THREADS + threadIdx.x; n0 < B; n0 += 2 * stride) {
+    const int64_t n1 = n0 + stride;
+    const bool v1 = n1 < B;
+    float w[2], y[2][K];
+    w[0] = __ldg(wt + n0); w[1] = v1 ? __ldg(wt + n1) : 0.f;
 #pragma unroll
-    for (int i = 0; i < K; i++) y[i] = __ldg(ybuf + n * K + i);
-    acc[0] += (double)w;
-    int s = 1;
+    for (int i = 0; i < K; i++) { y[0][i] = __ldg(ybuf + n0 * K + i); y[1][i] = v1 ? __ldg(ybuf + n1 * K + i) : 0.f; }
 #pragma unroll
-    for (int i = 0; i < K; i++) {
-      const float wy = w * y[i];
+    for (int u = 0; u < 2; u++) {
+      acc[0] += (double)w[u];
+      int s = 1;
 #pragma unroll
-      for (int j = 0; j <= i; j++) { acc[s] += (double)(wy * y[j]); s++; }
+      for (int i = 0; i < K; i++) {
+        const float wy = w[u] * y[u][i];
+#pragma unroll
+        for (int j = 0; j <= i; j++) { acc[s] += (double)(wy * y[u][j]); s++; }
+      }
     }
   }
-  __shared__ double red[8][NS2];
+  __shared__ double red[SY_THREADS / 32][NS2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int s = 0; s < NS2; s++) {
@@ -554,7 +564,7 @@ k_sums_y(const float* __restrict__ wt, const float* __restrict__ ybuf, int64_t B
   __syncthreads();
   if (threadIdx.x < NS2) {
     double v = 0.0;
-    for (int q = 0; q < 8; q++) v += red[q][threadIdx.x];
+    for (int q = 0; q < SY_THREADS / 32; q++) v += red[q][threadIdx.x];
     part2[(size_t)blockIdx.x * NS2 + threadIdx.x] = v;
   }
 }
@@ -562,7 +572,7 @@ k_sums_y(const float* __restrict__ wt, const float* __restrict__ ybuf, int64_t B
 // sums = [W, S1(k), E(k), S2(k(k+1)/2)] from the two partial arrays; one warp per sum, fixed (lane-strided, then
 // shuffle-tree) order
 __device__ __forceinline__ void reduce_tc_body(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2,
-                                               int K, double* sums) {
+                                               int K, double* sums, double* ssums = nullptr) {
   const int lane = threadIdx.x & 31;
   const int ns2 = 1 + K * (K + 1) / 2, ns = 1 + 2 * K + K * (K + 1) / 2;       // 34 sums for k = 6
   for (int s = threadIdx.x >> 5; s < ns; s += blockDim.x >> 5) {
@@ -575,7 +585,7 @@ __device__ __forceinline__ void reduce_tc_body(const double* __restrict__ part, 
       for (int b = lane; b < gx; b += 32) v += part[((size_t)net * gx + b) * 2 + which];
     }
     v = warp_sum(v);
-    if (lane == 0) sums[s] = v;
+    if (lane == 0) { sums[s] = v; if (ssums) ssums[s] = v; }
   }
 }
 __global__ void __launch_bounds__(1024)
@@ -588,10 +598,12 @@ __global__ void __launch_bounds__(1024)
 k_reduce_coef_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K, double* sums,
                  double beta, double alpha, EigW eigw, int sort, double* __restrict__ out, Coef* __restrict__ coef,
                  const float* __restrict__ mx, const float* __restrict__ nrm) {
-  reduce_tc_body(part, gx, part2, g2, K, sums);
-  __threadfence_block();
+  pdl_trigger();                     // phase 2's CTAs may come in and set up shared / tensor memory while this CTA works
+  pdl_wait();                        // k_sums_y (and with it phase 1) complete
+  __shared__ double ssums[1 + 2 * EPDE_MAX_K + EPDE_MAX_K * (EPDE_MAX_K + 1) / 2];      // the coefficient part reads the sums from here
+  reduce_tc_body(part, gx, part2, g2, K, sums, ssums);
   __syncthreads();
-  if (threadIdx.x < 32) coef_body<0>(sums, K, beta, alpha, eigw, sort, out, coef, mx, nrm);
+  if (threadIdx.x < 32) coef_body<0>(ssums, K, beta, alpha, eigw, sort, out, coef, mx, nrm);
 }
 
 }  // namespace tc

@@ -155,9 +155,6 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     for (int i = tid; i < L.total(); i += P2THREADS) sw[i] = src[i];
     for (int i = tid; i < P2G * IMT; i += P2THREADS) imgs[i] = 0.f;
     for (uint32_t i = tid; i < P2G * SG_BYTES / 4; i += P2THREADS) reinterpret_cast<float*>(sg)[i] = 0.f;
-    if (tid < 16) scs[tid] = coef->sc[net][tid];
-    if (tid >= 32 && tid < 40) scs[16 + tid - 32] = coef->fl[net][tid - 32];
-    if (tid == 40) { scs[26] = 1.f / coef->sc[net][1]; scs[27] = 1.f / coef->sc[net][12]; }      // 1 / s(g3), 1 / s(x)
   }
   if (tid == 0) {
     for (int i = 0; i < 2 * P2G; i++) mbar_init(bars + i, 1);                   // completed by tcgen05.commit
@@ -166,6 +163,15 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // Everything above is independent of the coefficient kernel, which this launch follows programmatically (PDL): the CTA
+  // is resident and set up while k_reduce_coef_tc / k_coef still runs.  Phase 1's outputs (pwt, stash, ybuf, xt, wt) were
+  // complete before that kernel started.
+  pdl_wait();
+  {
+    if (tid < 16) scs[tid] = coef->sc[net][tid];
+    if (tid >= 32 && tid < 40) scs[16 + tid - 32] = coef->fl[net][tid - 32];
+    if (tid == 40) { scs[26] = 1.f / coef->sc[net][1]; scs[27] = 1.f / coef->sc[net][12]; }      // 1 / s(g3), 1 / s(x)
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
