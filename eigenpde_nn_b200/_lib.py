@@ -18,6 +18,7 @@ ACT_IDS = {"Tanh": 0, "Sigmoid": 1, "Softplus": 2, "LogSigmoid": 3, "ELU": 4, "C
 FLAG_SORT = 1
 FLAG_DETERMINISTIC = 2
 FLAG_FFMA2 = 4          # fused path: FP32 FFMA2 kernel family instead of the tcgen05 family (include/eigenpde_b200.h)
+FLAG_GENERIC = 8        # never take the fused path (layer-wise generic family)
 ABI_VERSION = 3
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
@@ -115,7 +116,8 @@ def activation_id(activation_name) -> int:
                     % (activation_name, sorted(ACT_IDS)))
 
 
-def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, metric_ptr=None, ffma2=False) -> EpdeDesc:
+def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, metric_ptr=None, ffma2=False,
+              generic=False) -> EpdeDesc:
     """arch = [d, n_1, ..., n_{L-1}, 1] (src/pytorch_eigen_solver.py:352)."""
     if len(arch) - 1 > EPDE_MAX_LAYERS:
         raise EpdeError("too many layers")
@@ -124,6 +126,6 @@ def make_desc(arch, k, activation_name, d_pad, sort=True, deterministic=False, m
     for i, n in enumerate(arch):
         D.widths[i] = int(n)
     D.act_id = activation_id(activation_name)
-    D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0) | (FLAG_FFMA2 if ffma2 else 0)
+    D.flags = (FLAG_SORT if sort else 0) | (FLAG_DETERMINISTIC if deterministic else 0) | (FLAG_FFMA2 if ffma2 else 0) | (FLAG_GENERIC if generic else 0)
     D.metric = metric_ptr
     return D

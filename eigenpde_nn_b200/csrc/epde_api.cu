@@ -21,7 +21,8 @@ constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 
 constexpr int kFusedH = 20;
 // kernel family of the fused path: EPDE_FLAG_FFMA2 in the descriptor selects the FFMA2 kernels (epde_fused.cuh), the
 // default are the tcgen05 kernels (epde_tc_fused.cuh).  The choice travels with the descriptor: no process-wide state.
-inline int fused_impl(const epde_desc* D) { return (D->flags & EPDE_FLAG_FFMA2) ? 0 : 1; }
+// A per-row metric (MD alignment layer) is implemented by the FFMA2 kernels only.
+inline int fused_impl(const epde_desc* D) { return ((D->flags & EPDE_FLAG_FFMA2) || D->metric) ? 0 : 1; }
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
@@ -41,13 +42,14 @@ int check_desc(const epde_desc* D) {
 }
 
 bool fused_ok(const epde_desc* D) {
-  if (D->metric) return false;                  // per-row metric (MD alignment layer): generic family only
+  if (D->metric && (D->d > 2 * kFusedH || (D->flags & EPDE_FLAG_GENERIC))) return false;   // per-row metric: u0 / p live in 2 H shared-memory rows
+  if (D->flags & EPDE_FLAG_GENERIC) return false;
   if (D->n_layers != 4 || D->act_id != EPDE_ACT_TANH) return false;
   if (D->widths[1] != kFusedH || D->widths[2] != kFusedH || D->widths[3] != kFusedH) return false;
   if (D->k > 6) return false;
   if (D->d + 1 > 8 * 8) return false;           // tensor-core family: layer-1 k-steps 8 ks1 >= d + 1 with ks1 <= 8 (x staging rows TXR = 64)
   return pass2_smem_bytes<kFusedH>(D->d, D->d_pad) <= 227 * 1024 &&
-         (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + 4096 <= 200 * 1024;
+         (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + (D->metric ? (size_t)D->d * P1_US * 4 : 0) + 4096 <= 200 * 1024;
 }
 
 int64_t param_count(const epde_desc* D) {
@@ -106,10 +108,10 @@ __global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, d
 
 template <int K>
 cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt, const float* wt, int64_t B, int d,
-                         int d_pad, const float* pw, float* ybuf, double* part) {
+                         int d_pad, const float* pw, float* ybuf, double* part, const float* metric, const int64_t* idx) {
   cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part);
+  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part, metric, idx);
   return cudaGetLastError();
 }
 
@@ -155,14 +157,14 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
-  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
+  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + (D->metric ? (size_t)D->d * P1_US * 4 : 0);
   switch (D->k) {
-    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
-    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
-    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part); break;
+    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
   }
   if (e != cudaSuccess) return (int)e;
   k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums);
@@ -197,7 +199,7 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   cudaError_t e = cudaFuncSetAttribute(k_pass2<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
-                                                              W.coef, W.pg);
+                                                              W.coef, W.pg, D->metric, idx);
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   k_fin2<kFusedH><<<dim3(D->k, fin2_items<kFusedH>(D->d)), 1024, 0, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
   return (int)cudaGetLastError();

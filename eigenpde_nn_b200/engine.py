@@ -33,7 +33,7 @@ class StepEngine:
     """
 
     def __init__(self, X, weights, arch, k, activation_name, diag_coeff, beta, eig_w, sort=True,
-                 device=None, process_group=None, deterministic=False, metric=None, ffma2=False):
+                 device=None, process_group=None, deterministic=False, metric=None, ffma2=False, generic=False):
         if not torch.cuda.is_available():
             raise _lib.EpdeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.lib = _lib.lib()
@@ -52,7 +52,7 @@ class StepEngine:
             self.metric = metric.to(self.device, torch.float32).contiguous()
             assert self.metric.dim() == 3 and self.metric.shape[1] == self.d and self.metric.shape[2] == self.d
         self.desc = _lib.make_desc(self.arch, self.k, activation_name, self.d_pad, sort, deterministic,
-                                   self.metric.data_ptr() if self.metric is not None else None, ffma2=ffma2)
+                                   self.metric.data_ptr() if self.metric is not None else None, ffma2=ffma2, generic=generic)
         self.pg = process_group
         n = C.c_int64()
         _lib.check(self.lib.epde_param_count(C.byref(self.desc), C.byref(n)), "epde_param_count")

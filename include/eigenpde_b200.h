@@ -70,7 +70,10 @@ enum {
                                      Tanh): set = FP32 FFMA2 kernels (sample-pair threads, weights broadcast from shared
                                      memory); clear (default) = tcgen05 kernels (thread = TMEM lane = sample).  Both
                                      compute the same quantities to the same tolerance.  Must be the same in the
-                                     epde_step_partial / epde_step_finish pair of a step. */
+                                     epde_step_partial / epde_step_finish pair of a step.  With a per-row metric
+                                     (epde_desc.metric, d <= 40) the fused path always runs the FFMA2 kernels. */
+#define EPDE_FLAG_GENERIC 8u      /* never take the fused path: layer-wise generic family even for the reference
+                                     architecture (testing / A-B measurements) */
 
 typedef struct epde_desc {
   int32_t d;                            /* input dimension n_0 (data_set.tot_dim) */

@@ -487,12 +487,63 @@ def test_md_align_kernel_and_metric_step_vs_reference():
     assert np.abs(Xa[rows, :d].cpu().numpy() - xa_ref).max() <= 2e-6 * np.abs(xa_ref).max()       # fp32 storage
     assert np.abs(M[rows].cpu().numpy() - M_ref).max() <= 2e-6 * np.abs(M_ref).max()
     assert float(Xa[:, d:].abs().max()) == 0.0                                                       # padding columns
-    eng = StepEngine(Xa, torch.from_numpy(g["w"]), g["arch"], g["k"], g["act"], g["diag_coeff"], g["beta"], g["eig_w"],
-                     metric=M)
-    assert not eng.fused                        # per-row metric: generic family
-    res = eng.step(g["idx"], _flat(g["params"]), g["alpha"])
-    grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), g["arch"], g["k"])
-    check_step_against(g, res, TOL, grads)
+    for generic in (False, True):               # the fused kernels with the per-row metric, and the layer-wise family
+        eng = StepEngine(Xa, torch.from_numpy(g["w"]), g["arch"], g["k"], g["act"], g["diag_coeff"], g["beta"], g["eig_w"],
+                         metric=M, generic=generic)
+        assert eng.fused == (not generic)
+        res = eng.step(g["idx"], _flat(g["params"]), g["alpha"])
+        grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), g["arch"], g["k"])
+        check_step_against(g, res, TOL, grads)
+
+
+def _metric_case(seed, d, k, K, B, identity=False):
+    """Random symmetric positive definite per-row metrics M_r = A_r A_r^T + 0.1 I on top of a random case."""
+    c = _rand_case(seed, d, k, [20, 20, 20], K, 0 if identity else B, scale=0.4)
+    rng = np.random.default_rng(seed + 1)
+    A = 0.4 * rng.standard_normal((K, d, d))
+    M = np.einsum("rij,rkj->rik", A, A) + 0.1 * np.eye(d)[None]
+    c["metric"] = M.astype(np.float32).astype(np.float64)
+    c["w"] = np.exp(1.0 * rng.standard_normal(K)).astype(np.float32).astype(np.float64)
+    return c
+
+
+def _oracle_metric(c):
+    idx = c["idx"] if c["idx"] is not None else np.arange(c["X"].shape[0])
+    return closed_form.step(c["params"], c["X"][idx], c["w"][idx], c["diag_coeff"], c["beta"], c["alpha"], c["eig_w"],
+                            c["act"], metric=c["metric"][idx])
+
+
+@pytest.mark.parametrize("d,k,B", [(30, 2, 1000), (30, 2, 257), (30, 3, 37), (6, 1, 300), (33, 2, 513), (40, 2, 300),
+                                   (9, 6, 700), (30, 2, 10000)])
+def test_per_row_metric_fused_kernels_vs_oracle(d, k, B):
+    """The per-row metric (MD alignment layer) on the fused FFMA2 kernels: explicit u0 = W1^T g1, warp-wide
+    p = M_r u0, the extra g1 (x) p outer-product phase; ragged batches, d below / above one warp of columns."""
+    from eigenpde_nn_b200.engine import StepEngine
+    c = _metric_case(900 + d + B, d, k, 1200, B)
+    eng = StepEngine(c["X"], c["w"], c["arch"], c["k"], c["act"], c["diag_coeff"], c["beta"], c["eig_w"],
+                     metric=torch.from_numpy(c["metric"]))
+    assert eng.fused
+    _check(c, _oracle_metric(c), eng.step(c["idx"], _flat(c["params"]), c["alpha"]))
+
+
+def test_per_row_metric_identity_index_and_generic_family_agree():
+    from eigenpde_nn_b200.engine import StepEngine
+    c = _metric_case(77, 30, 2, 777, 0, identity=True)
+    ref = _oracle_metric(c)
+    for generic in (False, True):
+        eng = StepEngine(c["X"], c["w"], c["arch"], c["k"], c["act"], c["diag_coeff"], c["beta"], c["eig_w"],
+                         metric=torch.from_numpy(c["metric"]), generic=generic)
+        assert eng.fused == (not generic)
+        _check(c, ref, eng.step(None, _flat(c["params"]), c["alpha"]))
+
+
+def test_per_row_metric_too_wide_for_the_fused_rows_falls_back():
+    from eigenpde_nn_b200.engine import StepEngine
+    c = _metric_case(5, 42, 2, 400, 300)
+    eng = StepEngine(c["X"], c["w"], c["arch"], c["k"], c["act"], c["diag_coeff"], c["beta"], c["eig_w"],
+                     metric=torch.from_numpy(c["metric"]))
+    assert not eng.fused                        # u0 / p need d <= 40 shared-memory rows
+    _check(c, _oracle_metric(c), eng.step(c["idx"], _flat(c["params"]), c["alpha"]))
 
 
 def test_train_epilogue_equals_separate_calls():

@@ -1,5 +1,5 @@
 """MD mode (BASELINE config 3 shape WITH the alignment layer): one-time epde_md_align cost and the
-per-step time of the metric step on the generic family.  d = 30 (10 atoms), k = 2, K = 1e5 rows, B = 10 000."""
+per-step time of the metric step on the fused FFMA2 kernels and on the generic family.  d = 30 (10 atoms), k = 2, K = 1e5 rows, B = 10 000."""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch
@@ -33,15 +33,18 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 print("epde_md_align: %.2f ms for K = %d rows (kernel only; %.1f ms incl. upload/allocation), metric %.0f MB"
       % (e0.elapsed_time(e1) / 5, K, t_align * 1e3, M.numel() * 4 / 1e6))
-eng = StepEngine(Xa, torch.from_numpy(w), [d, 20, 20, 20, 1], k, "Tanh", diag, beta, [1.0, 0.8], metric=M)
-p = (0.5 * torch.randn(eng.n_params)).cuda()
+p = None
 idx = torch.randint(0, K, (B,), device="cuda")
-for _ in range(3): eng.step_device(idx, B, p, 20.0)
-e0.record()
-for _ in range(20): eng.step_device(idx, B, p, 20.0)
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 20
-print("MD-mode step (metric, generic family): %.3f ms per step at B = %d -> %.2f M samples/s" % (ms, B, B / ms / 1e3))
+for generic in (False, True):
+    eng = StepEngine(Xa, torch.from_numpy(w), [d, 20, 20, 20, 1], k, "Tanh", diag, beta, [1.0, 0.8], metric=M, generic=generic)
+    if p is None: p = (0.5 * torch.randn(eng.n_params)).cuda()
+    for _ in range(3): eng.step_device(idx, B, p, 20.0)
+    e0.record()
+    for _ in range(20): eng.step_device(idx, B, p, 20.0)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print("MD-mode step (per-row metric, %s): %.3f ms per step at B = %d -> %.2f M samples/s"
+          % ("generic layer-wise family" if generic else "fused FFMA2 kernels", ms, B, B / ms / 1e3))
 eng2 = StepEngine(Xa, torch.from_numpy(w), [d, 20, 20, 20, 1], k, "Tanh", diag, beta, [1.0, 0.8])
 for _ in range(3): eng2.step_device(idx, B, p, 20.0)
 e0.record()
