@@ -18,6 +18,7 @@ using namespace epde;
 namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
+constexpr int kMetricCtas = 4 * kMaxCtas;   // upper bound on k_metric's grid
 constexpr int kFusedH = 20;
 // kernel family of the fused path: EPDE_FLAG_FFMA2 in the descriptor selects the FFMA2 kernels (epde_fused.cuh), the
 // default are the tcgen05 kernels (epde_tc_fused.cuh).  The choice travels with the descriptor: no process-wide state.
@@ -49,7 +50,7 @@ bool fused_ok(const epde_desc* D) {
   if (D->k > 6) return false;
   if (D->d + 1 > 8 * 8) return false;           // tensor-core family: layer-1 k-steps 8 ks1 >= d + 1 with ks1 <= 8 (x staging rows TXR = 64)
   return pass2_smem_bytes<kFusedH>(D->d, D->d_pad) <= 227 * 1024 &&
-         (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + (D->metric ? (size_t)D->d * P1_US * 4 : 0) + 4096 <= 200 * 1024;
+         (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + 4096 <= 200 * 1024;
 }
 
 int64_t param_count(const epde_desc* D) {
@@ -65,6 +66,7 @@ struct FusedWs {
   float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
   float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh)
   float* stash;               // phase-1 intermediates of the tensor-core family (480 B per sample and net)
+  float* U; double* epart;    // per-row metric: u0 -> p of every net [k][tiles][d][256], k_metric's partial energy sums
   size_t total;
 };
 FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
@@ -82,7 +84,9 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.part2 = (double*)take((size_t)kMaxCtas * 32 * 8);
   W.mx = (float*)take((size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4);
   W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
-  W.stash = (float*)take(tc::stash_floats(B, D->k) * 4);
+  W.stash = (float*)take(D->metric ? 0 : tc::stash_floats(B, D->k) * 4);      // (a metric runs the FFMA2 kernels: no stash)
+  W.U = (float*)take(D->metric ? (size_t)D->k * ntl * D->d * GT * 4 : 0);
+  W.epart = (double*)take(D->metric ? (size_t)kMetricCtas * EPDE_MAX_K * 8 : 0);
   W.total = off;
   return W;
 }
@@ -98,20 +102,30 @@ int sm_count(int* out) {
 }
 
 // sum the per-CTA partials in CTA order -> sums[NS]
-__global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restrict__ sums) {
+// (+ per-row metric: the energy sums E_i = sums[1 + k + i] come from k_metric's partials epart[ne][k])
+__global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restrict__ sums,
+                              const double* __restrict__ epart = nullptr, int ne = 0, int k = 0) {
   const int s = threadIdx.x;
   if (s >= ns) return;
   double v = 0.0;
   for (int b = 0; b < nb; b++) v += part[(size_t)b * ns + s];
+  if (epart && s > k && s <= 2 * k)
+    for (int b = 0; b < ne; b++) v += epart[(size_t)b * k + (s - 1 - k)];
   sums[s] = v;
 }
 
 template <int K>
 cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt, const float* wt, int64_t B, int d,
-                         int d_pad, const float* pw, float* ybuf, double* part, const float* metric, const int64_t* idx) {
+                         int d_pad, const float* pw, float* ybuf, double* part, float* U) {
+  if (U) {
+    cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_pass1<kFusedH, K, true><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part, U);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part, metric, idx);
+  k_pass1<kFusedH, K><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part);
   return cudaGetLastError();
 }
 
@@ -157,17 +171,25 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
-  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4 + (D->metric ? (size_t)D->d * P1_US * 4 : 0);
+  const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
+  float* U = D->metric ? W.U : nullptr;
   switch (D->k) {
-    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
-    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
-    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
-    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
-    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
-    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, D->metric, idx); break;
+    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
   }
   if (e != cudaSuccess) return (int)e;
-  k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums);
+  int ne = 0;
+  if (D->metric) {      // p = M_r u0 in place in W.U, partial energy sums: one warp per sample over the whole GPU
+    ne = (int)((B + MET_THREADS / 32 - 1) / (MET_THREADS / 32));
+    if (ne > 4 * nsm) ne = 4 * nsm;
+    k_metric<0><<<ne, MET_THREADS, 0, st>>>(D->metric, idx, W.wt, B, D->d, D->k, W.U, (int64_t)((B + GT - 1) / GT), W.epart);
+    e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
+  }
+  k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums, D->metric ? W.epart : nullptr, ne, D->k);
   return (int)cudaGetLastError();
 }
 
@@ -196,10 +218,18 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   int gx = nsm / D->k; if (gx < 1) gx = 1;
   if (gx > ntiles) gx = (int)ntiles;
   const size_t smem = pass2_smem_bytes<kFusedH>(D->d, D->d_pad);
-  cudaError_t e = cudaFuncSetAttribute(k_pass2<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
-                                                              W.coef, W.pg, D->metric, idx);
+  cudaError_t e;
+  if (D->metric) {
+    e = cudaFuncSetAttribute(k_pass2<kFusedH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_pass2<kFusedH, true><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
+                                                                      W.coef, W.pg, W.U);
+  } else {
+    e = cudaFuncSetAttribute(k_pass2<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_pass2<kFusedH><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
+                                                                W.coef, W.pg);
+  }
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   k_fin2<kFusedH><<<dim3(D->k, fin2_items<kFusedH>(D->d)), 1024, 0, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
   return (int)cudaGetLastError();

@@ -288,20 +288,22 @@ __device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const flo
 // ---------------------------------------------------------------------------------------------
 // The energy of a sample is taken in the metric M_r = J diag(c) J^T of the alignment layer's Jacobian at data-set row r
 // (epde_md_align), a dense symmetric d x d matrix per ROW: the K = W1 diag(c) W1^T shortcut of the plain path does not
-// exist, so u0 = W1^T g1 is formed explicitly.  A thread (= sample pair) writes u0 into shared-memory rows
-// [feature][sample]; the product p = M u0 is then done by the WARP, one sample at a time: lane i owns p_i and walks
-// down column i of M (= row i, M is symmetric), so every load of the matrix is one coalesced row of d floats (a thread
-// walking its own two matrices would touch 32 cache lines per instruction).  u0_j is a shared-memory broadcast.  Only the
-// warp's own 64 samples are involved: __syncwarp, no CTA barrier.
+// exist, so u0 = W1^T g1 is formed explicitly.  MD batches are small (1e4 samples = 20 CTAs of sample-pair threads), and a
+// matrix product per sample inside those few CTAs is bound by memory latency (measured: 0.32 ms per step at B = 10000,
+// 0.20 of it in phase 1).  So the product is a kernel of its own with one WARP per sample - the whole GPU works on it:
+//   k_pass1<MD>  writes u0 of every net to  U[net][tile][j][256]      (the layout of the gathered x tiles)
+//   k_metric     p = M_r u0 in place (lane i owns p_i and walks down column i of the symmetric M: every load is one
+//                coalesced row; the matrix is read once for all k nets), e = u0 . p, fp64 partial sums of w e per CTA
+//   k_pass2<MD>  reads p back: t = W1 p, and the extra outer-product phase GM0: dW1 += (2 ebar g1) (x) p
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// u0_j = sum_o W1[o][j] g1[o] for j < d -> rows[j * stride + col] (float2: the thread's two samples)
+// u0_j = sum_o W1[o][j] g1[o] for j < d -> dst[j * stride] (float2: the thread's two samples)
 template <int H>
-__device__ __forceinline__ void u0_rows(const float* __restrict__ sW1T, const float2 (&g)[H], int d, float* __restrict__ rows,
-                                        int stride, int col) {
+__device__ __forceinline__ void u0_store(const float* __restrict__ sW1T, const float2 (&g)[H], int d, float* __restrict__ dst,
+                                         int stride) {
 #pragma unroll 2
   for (int j = 0; j < d; j++) {
     const float* wr = sW1T + j * H;
@@ -312,62 +314,87 @@ __device__ __forceinline__ void u0_rows(const float* __restrict__ sW1T, const fl
       s0 = ffma2(splat(wv.x), g[4 * q + 0], s0); s1 = ffma2(splat(wv.y), g[4 * q + 1], s1);
       s0 = ffma2(splat(wv.z), g[4 * q + 2], s0); s1 = ffma2(splat(wv.w), g[4 * q + 3], s1);
     }
-    *reinterpret_cast<float2*>(rows + (size_t)j * stride + col) = fadd2(s0, s1);
+    *reinterpret_cast<float2*>(dst + (size_t)j * stride) = fadd2(s0, s1);
   }
 }
-// rows[j * stride + c0 + s], s < 64: u0 of this warp's samples (d <= 64).  Returns e = u0^T M u0 of the calling thread's
-// two samples (lane l owns samples 2l, 2l + 1; their data-set rows are r0, r1); WRITE_P: p = M u0 replaces u0 in place.
-template <bool WRITE_P>
-__device__ __forceinline__ float2 metric_apply(float* __restrict__ rows, int stride, int c0, int d,
-                                               const float* __restrict__ metric, int64_t r0, int64_t r1) {
-  const int lane = threadIdx.x & 31;
+constexpr int MET_THREADS = 256;            // k_metric: 8 warps = 8 samples in flight per CTA
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(MET_THREADS)
+k_metric(const float* __restrict__ metric, const int64_t* __restrict__ idx, const float* __restrict__ wt, int64_t B, int d,
+         int K, float* __restrict__ U, int64_t ntiles, double* __restrict__ epart) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i0 = lane, i1 = lane + 32;
+  const bool h0 = i0 < d, h1 = i1 < d;                   // d <= 64
   const size_t dd = (size_t)d * d;
-  float2 e = make_float2(0.f, 0.f);
+  double acc[EPDE_MAX_K];
+#pragma unroll
+  for (int q = 0; q < EPDE_MAX_K; q++) acc[q] = 0.0;
+  const int64_t nwarps = (int64_t)gridDim.x * (MET_THREADS / 32);
 #pragma unroll 1
-  for (int s = 0; s < 64; s++) {
-    const int64_t r = __shfl_sync(0xffffffffu, (s & 1) ? r1 : r0, s >> 1);
-    const float* M = metric + (size_t)r * dd;
-    float* col = rows + c0 + s;
-    float p0 = 0.f, p1 = 0.f;
-    if (d <= 32) {
-      const int ii = i0 < d ? i0 : d - 1;            // idle lanes repeat the last column (no divergence in the loop)
-#pragma unroll 6
-      for (int j = 0; j < d; j++) p0 = fmaf(__ldg(M + j * d + ii), col[(size_t)j * stride], p0);
-    } else {
-      const int ii = i1 < d ? i1 : d - 1;
-#pragma unroll 4
-      for (int j = 0; j < d; j++) {
-        const float uj = col[(size_t)j * stride];
-        p0 = fmaf(__ldg(M + j * d + i0), uj, p0);
-        p1 = fmaf(__ldg(M + j * d + ii), uj, p1);
+  for (int64_t n = (int64_t)blockIdx.x * (MET_THREADS / 32) + warp; n < B; n += nwarps) {
+    const float* M = metric + (size_t)(idx ? __ldg(idx + n) : n) * dd;
+    const float wn = __ldg(wt + n);
+    const int64_t tile = n / GT;
+    const int c = (int)(n % GT);
+    float u0[EPDE_MAX_K], u1[EPDE_MAX_K], p0[EPDE_MAX_K], p1[EPDE_MAX_K];
+#pragma unroll
+    for (int q = 0; q < EPDE_MAX_K; q++) {
+      u0[q] = 0.f; u1[q] = 0.f; p0[q] = 0.f; p1[q] = 0.f;
+      if (q < K) {
+        const float* Uq = U + ((size_t)(q * ntiles + tile) * d) * GT + c;
+        if (h0) u0[q] = Uq[(size_t)i0 * GT];
+        if (h1) u1[q] = Uq[(size_t)i1 * GT];
       }
     }
-    float es = (i0 < d) ? col[(size_t)i0 * stride] * p0 : 0.f;
-    if (i1 < d) es = fmaf(col[(size_t)i1 * stride], p1, es);
-    es = warp_sum_f(es);
-    if (lane == (s >> 1)) { if (s & 1) e.y = es; else e.x = es; }
-    if (WRITE_P) {
-      __syncwarp();                                  // every lane has read u0 of this sample
-      if (i0 < d) col[(size_t)i0 * stride] = p0;
-      if (i1 < d) col[(size_t)i1 * stride] = p1;
+    const int c0 = h0 ? i0 : d - 1, c1 = h1 ? i1 : d - 1;          // idle lanes repeat the last column
+#pragma unroll 4
+    for (int j = 0; j < d; j++) {
+      const float m0 = __ldg(M + (size_t)j * d + c0);
+      const float m1 = (d > 32) ? __ldg(M + (size_t)j * d + c1) : 0.f;
+#pragma unroll
+      for (int q = 0; q < EPDE_MAX_K; q++) {
+        if (q < K) {
+          const float uj = __shfl_sync(0xffffffffu, j < 32 ? u0[q] : u1[q], j & 31);
+          p0[q] = fmaf(m0, uj, p0[q]); p1[q] = fmaf(m1, uj, p1[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < EPDE_MAX_K; q++) {
+      if (q < K) {
+        const float es = warp_sum_f((h0 ? u0[q] * p0[q] : 0.f) + (h1 ? u1[q] * p1[q] : 0.f));
+        acc[q] += (double)(wn * es);
+        float* Uq = U + ((size_t)(q * ntiles + tile) * d) * GT + c;
+        if (h0) Uq[(size_t)i0 * GT] = p0[q];
+        if (h1) Uq[(size_t)i1 * GT] = p1[q];
+      }
     }
   }
-  __syncwarp();
-  return e;
+  __shared__ double red[MET_THREADS / 32][EPDE_MAX_K];
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < EPDE_MAX_K; q++) red[warp][q] = acc[q];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < K) {
+    double v = 0.0;
+    for (int w = 0; w < MET_THREADS / 32; w++) v += red[w][threadIdx.x];
+    epart[(size_t)blockIdx.x * K + threadIdx.x] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_pass1
 // ---------------------------------------------------------------------------------------------
 constexpr int P1_THREADS = 256;
-constexpr int P1_US = 2 * P1_THREADS;      // floats per u0 row of the metric path (two samples per thread)
 
-template <int H, int K>
+// MD: per-row metric - u0 = W1^T g1 of every net goes to U[net][tile][j][256] for k_metric, which also produces the energy
+// sums (this kernel then leaves the E slots of its partial sums at zero)
+template <int H, int K, bool MD = false>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad,
         const float* __restrict__ pw, float* __restrict__ ybuf, double* __restrict__ part,
-        const float* __restrict__ metric = nullptr, const int64_t* __restrict__ idx = nullptr) {
+        float* __restrict__ U = nullptr) {
   constexpr int NS = 1 + 2 * K + K * (K + 1) / 2;
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
@@ -381,21 +408,13 @@ k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, i
   for (int s = 0; s < NS; s++) acc[s] = 0.0;
 
   const int64_t npairs = (B + 1) >> 1;
-  float* su = sw + K * pwn;                         // metric path: u0 rows [d][P1_US]
-  // whole warps stay in the loop (the metric path works warp-wide): lanes beyond the last pair repeat it with weight 0
-  for (int64_t pb = (int64_t)blockIdx.x * P1_THREADS + (threadIdx.x & ~31); pb < npairs; pb += (int64_t)gridDim.x * P1_THREADS) {
-    const bool act = pb + (threadIdx.x & 31) < npairs;
-    const int64_t p = act ? pb + (threadIdx.x & 31) : npairs - 1;
+  const int64_t ntiles = (B + GT - 1) / GT;
+  for (int64_t p = (int64_t)blockIdx.x * P1_THREADS + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * P1_THREADS) {
     const int64_t n0 = 2 * p, n1 = 2 * p + 1;
-    const bool v1 = act && n1 < B;
+    const bool v1 = n1 < B;
     const float2 w01 = __ldg(reinterpret_cast<const float2*>(wt + n0));     // wt is padded to whole tiles
-    const float w0 = act ? w01.x : 0.f, w1 = act ? w01.y : 0.f;
+    const float w0 = w01.x, w1 = w01.y;
     const float* xcol = xt + (size_t)(n0 / GT) * d_pad * GT + (n0 % GT);
-    int64_t r0 = 0, r1 = 0;                         // data-set rows of the two samples (metric path)
-    if (metric) {
-      const int64_t m1 = n1 < B ? n1 : B - 1;
-      r0 = idx ? __ldg(idx + n0) : n0; r1 = idx ? __ldg(idx + m1) : m1;
-    }
     float2 yv[K], ev[K];
 #pragma unroll 1
     for (int net = 0; net < K; net++) {
@@ -411,10 +430,9 @@ k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, i
       zero2(u); mv_acc<H, H>(s + L.W2(), g, u);         // u1 = W2^T g2
       dtanh_mul<H>(a1, u, g);                           // g1
       float2 e;
-      if (metric) {                                     // e = u0^T M_r u0, u0 = W1^T g1
-        u0_rows<H>(s + L.W1c(), g, d, su, P1_US, 2 * (int)threadIdx.x);
-        __syncwarp();
-        e = metric_apply<false>(su, P1_US, 64 * ((int)threadIdx.x >> 5), d, metric, r0, r1);
+      if (MD) {                                         // u0 = W1^T g1 -> U; e = u0^T M_r u0 is k_metric's
+        u0_store<H>(s + L.W1c(), g, d, U + ((size_t)(net * ntiles + n0 / GT) * d) * GT + (n0 % GT), GT);
+        e = make_float2(0.f, 0.f);
       } else {
         zero2(u); mv_acc<H, H>(s + L.Km(), g, u);       // t = K g1
         float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
@@ -422,7 +440,7 @@ k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, i
         for (int o = 0; o < H; o += 2) { e0 = ffma2(g[o], u[o], e0); e1 = ffma2(g[o + 1], u[o + 1], e1); }
         e = fadd2(e0, e1);                              // sum_j c_j (d_j f)^2 = g1^T K g1
       }
-      if (act) ybuf[n0 * K + net] = y.x;
+      ybuf[n0 * K + net] = y.x;
       if (v1) ybuf[n1 * K + net] = y.y;
 #pragma unroll
       for (int q = 0; q < K; q++) if (q == net) { yv[q] = y; ev[q] = e; }
@@ -585,12 +603,11 @@ __device__ __forceinline__ void row_sum(const float* __restrict__ row, float* __
   *out += (s.x + s.y) + (s.z + s.w);
 }
 
-template <int H>
+template <int H, bool MD = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
         int d, int d_pad, int K, const float* __restrict__ pw, const float* __restrict__ ybuf,
-        const Coef* __restrict__ coef, float* __restrict__ pg,
-        const float* __restrict__ metric = nullptr, const int64_t* __restrict__ idx = nullptr) {
+        const Coef* __restrict__ coef, float* __restrict__ pg, const float* __restrict__ U = nullptr) {
   static_assert(H == 20, "outer-product tiling (4x5 tiles, row stride 5) is written for H = 20");
   extern __shared__ float4 smem4[];
   const RowMap<H> R(d);
@@ -681,25 +698,21 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.G1() + o) = g[o];
       const float2 e2 = make_float2(2.f * ebar.x, 2.f * ebar.y);
-      ROW2(R.EB()) = metric ? e2 : ebar;
+      ROW2(R.EB()) = MD ? e2 : ebar;
       // ---- E-sweep, layer 1:  gbar1 = 2 ebar K g1
-      if (metric) {
-        // per-row metric: gbar1 = 2 ebar W1 p with p = M_r u0, u0 = W1^T g1, and dW1 += (2 ebar g1) (x) p (there is no
-        // Gamma shortcut).  u0 -> p in place in the rows of U1 / U2 (free until ubar1 is written; d <= 2 H), then the
-        // extra outer-product phase GM0 over the whole tile, with t = W1 p parked in the (still free) S4 rows.
-        int64_t r0, r1;
-        {
-          const int64_t n0 = tile * P2_T + col;
-          const int64_t m0 = n0 < B ? n0 : B - 1, m1 = n0 + 1 < B ? n0 + 1 : B - 1;
-          r0 = idx ? __ldg(idx + m0) : m0; r1 = idx ? __ldg(idx + m1) : m1;
-        }
-        u0_rows<H>(sw + L.W1c(), g, d, rows + (size_t)R.U1() * P2_TS, P2_TS, col);
-        __syncwarp();
-        metric_apply<true>(rows + (size_t)R.U1() * P2_TS, P2_TS, 64 * (tid >> 5), d, metric, r0, r1);
+      if (MD) {
+        // per-row metric: gbar1 = 2 ebar W1 p with p = M_r u0 (k_metric left it in U), and dW1 += (2 ebar g1) (x) p (there
+        // is no Gamma shortcut).  p goes into the rows of U1 / U2 (free until ubar1 is written; d <= 2 H) for the extra
+        // outer-product phase GM0 over the whole tile, with t = W1 p parked in the (still free) S4 rows.
+        const float* Pn = U + ((size_t)(net * ntiles + tile) * d) * GT + col;
+        const bool pv0 = tile * P2_T + col < B, pv1 = tile * P2_T + col + 1 < B;
         zero2(u);
 #pragma unroll 2
         for (int j = 0; j < d; j++) {                                  // t = W1 p
-          const float2 pj = ROW2(R.U1() + j);
+          float2 pj = __ldg(reinterpret_cast<const float2*>(Pn + (size_t)j * GT));
+          if (!pv0) pj.x = 0.f;                                        // samples beyond B: U holds nothing for them
+          if (!pv1) pj.y = 0.f;
+          ROW2(R.U1() + j) = pj;
           const float* wr = sw + L.W1c() + j * H;
 #pragma unroll
           for (int q = 0; q < H / 4; q++) {
@@ -770,7 +783,7 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
       constexpr int SG = P2_T / P2_NG;
       for (int wk = tid; wk < NU * P2_NG; wk += P2_THREADS) {
         const int grp = wk / NU, un = wk % NU, job = un / UPJ, t = un % UPJ;
-        if (metric && job == 0) continue;          // no Gamma with a per-row metric (GM0 did the g1 (x) ubar0 term)
+        if (MD && job == 0) continue;              // no Gamma with a per-row metric (GM0 did the g1 (x) ubar0 term)
         const int prow = (job == 0) ? R.G1() : (job == 1) ? R.G2() : R.G3();
         const int qrow = (job == 0) ? R.G1() : (job == 1) ? R.U1() : R.U2();
         const int srow = (job == 0) ? R.EB() : R.ONE();
