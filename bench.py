@@ -298,7 +298,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    exchange = "none" if world == 1 else ("peer" if eng._exchange is not None else "nccl")
+    exchange = "none" if world == 1 else (("peer-folded" if eng._fold_exchange() else "peer") if eng._exchange is not None else "nccl")
     # ---- N > 1: the sharded step against a single-rank step on the union batch (same kernels, no exchange) -----------
     parity = None
     if world > 1:
@@ -415,7 +415,9 @@ def main():
         "config": {"workload": "ex1_50d_k%d" % KNETS, "d": D, "k": KNETS, "arch": ARCH, "activation": "Tanh",
                    "batch_per_gpu": B, "global_batch": world * B, "dataset_rows": K_DATA,
                    "parallelism": ("dp%d (batch sharded by contiguous slices; 2 small all-reduces per step: %s)" % (
-                       world, "one-shot NVLink peer-memory kernel epde_peer_allreduce" if exchange == "peer" else "NCCL"))
+                       world, {"peer": "one-shot NVLink peer-memory kernel epde_peer_allreduce",
+                               "peer-folded": "NVLink peer-memory exchanges inside the step's own kernels (epde_step_sharded: "
+                                              "k_reduce_coef_tc and the last CTA of k_fin2), no exchange launch"}.get(exchange, "NCCL")))
                    if world > 1 else "single GPU", "exchange": exchange,
                    "l2": "inputs larger than L2: 872 MB data set gathered by fresh random indices each step"},
         "loss": float(out_h[0]), "eig_vals": [float(v) for v in out_h[4:4 + KNETS]],
@@ -443,8 +445,9 @@ def main():
                              + ("every rank jumps ahead to its slice of the %d-draw global batch (x^J mod the characteristic "
                                 "polynomial, epde_mt_jump_device) and generates only its own %d draws" % (world * B, B)
                                 if world > 1 else "%d draws per step" % B)},
-        # per step: memset, k_gather128, k_pack_tc, k_pass1_tc, k_sums_y, k_reduce_tc, k_coef, k_pass2_tc, k_fin2 (+ 2 exchange kernels)
-        "gpu_launches": (8 + (2 if world > 1 else 0)) * args.steps, "clocks": clocks,
+        # kernels per step: k_pack_tc, k_gather128, k_pass1_tc, k_sums_y, k_reduce_coef_tc, k_pass2_tc, k_fin2 - also with N > 1 when the
+        # exchanges are folded into k_reduce_coef_tc / k_fin2; otherwise k_reduce_tc + k_coef and two exchange launches (10)
+        "gpu_launches": (7 if exchange in ("none", "peer-folded") else 10) * args.steps, "clocks": clocks,
     }
     if parity is not None:
         line["parity"] = parity

@@ -19,10 +19,10 @@ FLAG_SORT = 1
 FLAG_DETERMINISTIC = 2
 FLAG_FFMA2 = 4          # fused path: FP32 FFMA2 kernel family instead of the tcgen05 family (include/eigenpde_b200.h)
 FLAG_GENERIC = 8        # never take the fused path (layer-wise generic family)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
-           "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_forward",
+           "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_step_sharded", "epde_forward",
            "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_mt_jump_poly", "epde_mt_jump_device",
            "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
            "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_train_epilogue64", "epde_peer_allreduce", "epde_peer_allreduce_graph"]
@@ -31,6 +31,11 @@ EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_nu
 class EpdeDesc(C.Structure):
     _fields_ = [("d", C.c_int32), ("d_pad", C.c_int32), ("k", C.c_int32), ("n_layers", C.c_int32),
                 ("widths", C.c_int32 * (EPDE_MAX_LAYERS + 1)), ("act_id", C.c_int32), ("flags", C.c_uint32), ("metric", C.c_void_p)]
+
+
+class EpdePeer(C.Structure):
+    _fields_ = [("d_peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("d_epoch", C.c_void_p),
+                ("slot_bytes", C.c_int64)]
 
 
 class EpdeError(RuntimeError):
@@ -59,6 +64,8 @@ def lib():
         L.epde_step_partial.argtypes = [dp, vp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
         L.epde_step_finish.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, vp, sz, vp, vp, vp]
         L.epde_step.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp, vp]
+        L.epde_step_sharded.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp,
+                                        C.POINTER(EpdePeer), vp]
         L.epde_forward.argtypes = [dp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
         L.epde_minibatch_indices.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, vp]
         L.epde_minibatch_indices_device.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]

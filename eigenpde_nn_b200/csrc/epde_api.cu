@@ -18,7 +18,8 @@ using namespace epde;
 namespace {
 
 constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
-constexpr int kMetricCtas = 4 * kMaxCtas;   // upper bound on k_metric's grid
+constexpr int kMxWords = 2 + kMxPerNet * EPDE_MAX_K;      // maxima (floats), followed by one ticket word
+constexpr int kMetricCtas = 16 * kMaxCtas;  // upper bound on k_metric's grid
 constexpr int kFusedH = 20;
 // kernel family of the fused path: EPDE_FLAG_FFMA2 in the descriptor selects the FFMA2 kernels (epde_fused.cuh), the
 // default are the tcgen05 kernels (epde_tc_fused.cuh).  The choice travels with the descriptor: no process-wide state.
@@ -64,7 +65,7 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 // ---- workspace ------------------------------------------------------------------------------
 struct FusedWs {
   float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
-  float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh)
+  float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh); mx is followed by k_fin2's ticket word
   float* stash;               // phase-1 intermediates of the tensor-core family (480 B per sample and net)
   float* U; double* epart;    // per-row metric: u0 -> p of every net [k][tiles][d][256], k_metric's partial energy sums
   size_t total;
@@ -82,7 +83,7 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.wt = (float*)take(ntl * GT * 4);
   W.pwt = (float*)take((size_t)D->k * tc::pack_floats(D->d) * 4);
   W.part2 = (double*)take((size_t)kMaxCtas * 32 * 8);
-  W.mx = (float*)take((size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4);
+  W.mx = (float*)take((size_t)(kMxWords + 1) * 4);
   W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
   W.stash = (float*)take(D->metric ? 0 : tc::stash_floats(B, D->k) * 4);      // (a metric runs the FFMA2 kernels: no stash)
   W.U = (float*)take(D->metric ? (size_t)D->k * ntl * D->d * GT * 4 : 0);
@@ -103,15 +104,19 @@ int sm_count(int* out) {
 
 // sum the per-CTA partials in CTA order -> sums[NS]
 // (+ per-row metric: the energy sums E_i = sums[1 + k + i] come from k_metric's partials epart[ne][k])
-__global__ void k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restrict__ sums,
-                              const double* __restrict__ epart = nullptr, int ne = 0, int k = 0) {
-  const int s = threadIdx.x;
-  if (s >= ns) return;
-  double v = 0.0;
-  for (int b = 0; b < nb; b++) v += part[(size_t)b * ns + s];
-  if (epart && s > k && s <= 2 * k)
-    for (int b = 0; b < ne; b++) v += epart[(size_t)b * k + (s - 1 - k)];
-  sums[s] = v;
+// One warp per sum: the lanes stride over the partial rows, a fixed shuffle tree adds the lane sums.
+__global__ void __launch_bounds__(1024)
+k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restrict__ sums,
+              const double* __restrict__ epart = nullptr, int ne = 0, int k = 0) {
+  const int lane = threadIdx.x & 31;
+  for (int s = threadIdx.x >> 5; s < ns; s += blockDim.x >> 5) {
+    double v = 0.0;
+    for (int b = lane; b < nb; b += 32) v += part[(size_t)b * ns + s];
+    if (epart && s > k && s <= 2 * k)
+      for (int b = lane; b < ne; b += 32) v += epart[(size_t)b * k + (s - 1 - k)];
+    v = warp_sum(v);
+    if (lane == 0) sums[s] = v;
+  }
 }
 
 template <int K>
@@ -158,7 +163,7 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   cudaError_t e;
   if (impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
   else {
-    e = cudaMemsetAsync(W.mx, 0, (size_t)(2 + kMxPerNet * EPDE_MAX_K) * 4, st);     // maxima are gathered with atomicMax
+    e = cudaMemsetAsync(W.mx, 0, (size_t)(kMxWords + 1) * 4, st);     // maxima are gathered with atomicMax; + k_fin2's ticket
     if (e != cudaSuccess) return (int)e;
     rc = tc::pack(D->d, D->k, params, diag, W.pwt, W.nrm, st);
     if (rc) return rc;
@@ -185,23 +190,25 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   int ne = 0;
   if (D->metric) {      // p = M_r u0 in place in W.U, partial energy sums: one warp per sample over the whole GPU
     ne = (int)((B + MET_THREADS / 32 - 1) / (MET_THREADS / 32));
-    if (ne > 4 * nsm) ne = 4 * nsm;
+    if (ne > 16 * nsm) ne = 16 * nsm;
     k_metric<0><<<ne, MET_THREADS, 0, st>>>(D->metric, idx, W.wt, B, D->d, D->k, W.U, (int64_t)((B + GT - 1) / GT), W.epart);
     e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
   }
-  k_reduce_part<<<1, 64, 0, st>>>(W.part, grid, num_sums(D->k), sums, D->metric ? W.epart : nullptr, ne, D->k);
+  k_reduce_part<<<1, 1024, 0, st>>>(W.part, grid, num_sums(D->k), sums, D->metric ? W.epart : nullptr, ne, D->k);
   return (int)cudaGetLastError();
 }
 
 int fused_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                  const float* params, const float* diag, double beta, double alpha, const EigW& ew,
-                 const double* sums, void* ws, double* out, float* grad, cudaStream_t st, const Deferred* df = nullptr) {
+                 const double* sums, void* ws, double* out, float* grad, cudaStream_t st, const Deferred* df = nullptr,
+                 const Peer* peer = nullptr) {
+  const Peer none = {nullptr, 0, 1, nullptr, 0};
   FusedWs W = fused_ws(D, B, ws);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   const int impl = fused_impl(D);
   if (impl == 1 && df && df->on) {
     rc = tc::reduce_coef(W.part, df->gx, W.part2, df->g2, D->k, const_cast<double*>(sums), beta, alpha, ew,
-                         (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef, W.mx, W.nrm, st);
+                         (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef, W.mx, W.nrm, st, peer);
     if (rc) return rc;
   } else
   k_coef<0><<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, W.coef,
@@ -211,7 +218,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
     rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
     if (rc) return rc;
     cudaError_t e2 = launch_pdl(k_fin2<kFusedH>, dim3(D->k, fin2_items<kFusedH>(D->d)), dim3(1024), 0, st, (const float*)W.pg, gx,
-                                D->k, D->d, D->d_pad, params, diag, grad);
+                                D->k, D->d, D->d_pad, params, diag, grad, peer ? *peer : none,
+                                reinterpret_cast<uint32_t*>(W.mx) + kMxWords);
     return (int)(e2 != cudaSuccess ? e2 : cudaGetLastError());
   }
   const int64_t ntiles = (B + P2_T - 1) / P2_T;
@@ -231,7 +239,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
                                                                 W.coef, W.pg);
   }
   e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
-  k_fin2<kFusedH><<<dim3(D->k, fin2_items<kFusedH>(D->d)), 1024, 0, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad);
+  k_fin2<kFusedH><<<dim3(D->k, fin2_items<kFusedH>(D->d)), 1024, 0, st>>>(W.pg, gx, D->k, D->d, D->d_pad, params, diag, grad, none,
+                                                                           nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -247,12 +256,7 @@ int check_common(const epde_desc* D, const float* X, const float* w, int64_t B, 
 }
 
 // ---- one-shot all-reduce over NVLink peer memory (the two tiny exchanges of the sharded step) --------------------------
-// Every rank owns one symmetric buffer [256 B of flags = 2 parities x 32 ranks x uint32 | 2 parities x world slots x
-// slot_bytes]; world <= 32 (the flag block holds exactly 2 x 32 flags).  A call (epoch e, parity
-// e & 1) stores this rank's payload into slot[rank] of EVERY rank's buffer with plain peer stores, fences, raises
-// flag[parity][rank] = e in every rank's buffer, waits until all world flags of its OWN buffer show e, and sums the world
-// slots in rank order (the same order on every rank: bit-identical results everywhere).  A rank cannot run two epochs
-// ahead of a peer (it needs that peer's flag for e+1, raised only after the peer finished e), so two parities suffice.
+// (protocol: peer_allreduce_block in epde_common.cuh)
 template <typename T>
 __global__ void __launch_bounds__(1024)
 k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t epoch_arg, uint32_t* __restrict__ epoch_ctr,
@@ -260,30 +264,8 @@ k_peer_allreduce(char* const* __restrict__ bufs, int rank, int world, uint32_t e
   // epoch: an argument, or (epoch_ctr != NULL) a counter in device memory that every call advances by one -- the launch
   // arguments are then invariant and the exchange can sit inside a replayed CUDA graph
   const uint32_t epoch = epoch_ctr ? *epoch_ctr + 1u : epoch_arg;
-  const int par = epoch & 1;
-  const int64_t data_off = 256 + ((int64_t)par * world + rank) * slot_bytes;
-  for (int p = 0; p < world; p++) {
-    T* slot = reinterpret_cast<T*>(bufs[p] + data_off);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = src[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < world) {
-    volatile uint32_t* theirs = reinterpret_cast<volatile uint32_t*>(bufs[threadIdx.x]) + par * world + rank;
-    *theirs = epoch;
-    __threadfence_system();
-    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(bufs[rank]) + par * world + threadIdx.x;
-    int spin = 0;
-    while (*mine != epoch) { __nanosleep(128); if (++spin > (1 << 28)) __trap(); }   // bounded (~1 min): a lost peer traps
-  }
-  __syncthreads();
-  __threadfence_system();
-  const char* base = bufs[rank] + 256 + (int64_t)par * world * slot_bytes;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    T v = 0;
-    for (int p = 0; p < world; p++) v += reinterpret_cast<const volatile T*>(base + (int64_t)p * slot_bytes)[i];
-    dst[i] = v;
-  }
+  const Peer P = {bufs, rank, world, epoch_ctr, (long long)slot_bytes};
+  peer_allreduce_block<T>(P, epoch, src, dst, (T*)nullptr, n);
   if (epoch_ctr && threadIdx.x == 0) *epoch_ctr = epoch;      // every thread read it before the first __syncthreads
 }
 
@@ -384,6 +366,26 @@ int epde_step(const epde_desc* D, const float* X, const float* w, const int64_t*
   }
   rc = epde_step_partial(D, X, w, idx, B, params, diag, ws, ws_bytes, sums, stream); if (rc) return rc;
   return epde_step_finish(D, X, w, idx, B, params, diag, beta, alpha, h_eig_w, sums, ws, ws_bytes, out, grad, stream);
+}
+
+int epde_step_sharded(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                      const float* params, const float* diag, double beta, double alpha, const double* h_eig_w,
+                      void* ws, size_t ws_bytes, double* out, float* grad, const epde_peer* peer, void* stream) {
+  int rc = check_common(D, X, w, B, params, diag, ws, ws_bytes); if (rc) return rc;
+  if (!out || !h_eig_w || !grad || !peer || !peer->d_peer_bufs || !peer->d_epoch) return EPDE_ERR_NULL;
+  if (peer->world < 2 || peer->world > 32 || peer->rank < 0 || peer->rank >= peer->world || (peer->slot_bytes & 15))
+    return EPDE_ERR_ARG;
+  if (!fused_ok(D) || fused_impl(D) != 1) return EPDE_ERR_UNSUPPORTED;      // tensor-core family only
+  if (param_count(D) * 4 > peer->slot_bytes || num_sums(D->k) * 8 > peer->slot_bytes) return EPDE_ERR_ARG;
+  size_t need; epde_workspace_bytes(D, B, &need);
+  double* sums = (double*)((char*)ws + need - kSumsTail);
+  EigW ew; memset(&ew, 0, sizeof(ew));
+  for (int i = 0; i < D->k; i++) ew.v[i] = h_eig_w[i];
+  const Peer P = {reinterpret_cast<char* const*>(peer->d_peer_bufs), peer->rank, peer->world, peer->d_epoch,
+                  (long long)peer->slot_bytes};
+  Deferred df = {1, 0, 0};
+  rc = fused_partial(D, X, w, idx, B, params, diag, ws, sums, (cudaStream_t)stream, &df); if (rc) return rc;
+  return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, (cudaStream_t)stream, &df, &P);
 }
 
 int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t B, const float* params,

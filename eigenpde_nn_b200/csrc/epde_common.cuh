@@ -111,6 +111,49 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// ---- one-shot all-reduce over NVLink peer memory, executed by ONE CTA (all of its threads) ----------------------------
+// Every rank owns one symmetric buffer [256 B of flags = 2 parities x 32 ranks x uint32 | 2 parities x world slots x
+// slot_bytes]; world <= 32.  A call (epoch e = *epoch_ctr + 1, parity e & 1) stores this rank's payload into slot[rank] of
+// EVERY rank's buffer with plain peer stores, fences, raises flag[parity][rank] = e in every rank's buffer, waits until all
+// world flags of its OWN buffer show e, and sums the world slots in rank order (the same order on every rank: bit-identical
+// results everywhere).  A rank cannot run two epochs ahead of a peer (it needs that peer's flag for e + 1, raised only
+// after the peer finished e), so two parities suffice.  The epoch counter lives in device memory and is advanced by the
+// call: launch arguments never change, the exchange can sit inside a replayed CUDA graph - or inside another kernel.
+struct Peer {
+  char* const* bufs;        // device array of `world` pointers (NULL: single rank, no exchange)
+  int rank, world;
+  uint32_t* epoch;          // device counter
+  long long slot_bytes;
+};
+template <typename T>
+__device__ __forceinline__ void peer_allreduce_block(const Peer& P, uint32_t epoch, const T* src, T* dst, T* dst2, int n) {
+  const int par = epoch & 1;
+  const long long data_off = 256 + ((long long)par * P.world + P.rank) * P.slot_bytes;
+  for (int p = 0; p < P.world; p++) {
+    T* slot = reinterpret_cast<T*>(P.bufs[p] + data_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = *reinterpret_cast<const volatile T*>(src + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
+    volatile uint32_t* theirs = reinterpret_cast<volatile uint32_t*>(P.bufs[threadIdx.x]) + par * P.world + P.rank;
+    *theirs = epoch;
+    __threadfence_system();
+    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(P.bufs[P.rank]) + par * P.world + threadIdx.x;
+    int spin = 0;
+    while (*mine != epoch) { __nanosleep(128); if (++spin > (1 << 28)) __trap(); }   // bounded (~1 min): a lost peer traps
+  }
+  __syncthreads();
+  __threadfence_system();
+  const char* base = P.bufs[P.rank] + 256 + (long long)par * P.world * P.slot_bytes;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    T v = 0;
+    for (int p = 0; p < P.world; p++) v += reinterpret_cast<const volatile T*>(base + (long long)p * P.slot_bytes)[i];
+    dst[i] = v;
+    if (dst2) dst2[i] = v;
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -347,15 +347,29 @@ k_metric(const float* __restrict__ metric, const int64_t* __restrict__ idx, cons
       }
     }
     const int c0 = h0 ? i0 : d - 1, c1 = h1 ? i1 : d - 1;          // idle lanes repeat the last column
-#pragma unroll 4
-    for (int j = 0; j < d; j++) {
-      const float m0 = __ldg(M + (size_t)j * d + c0);
-      const float m1 = (d > 32) ? __ldg(M + (size_t)j * d + c1) : 0.f;
+    if (d <= 32) {      // all d loads of the column in flight at once (a rolled loop is bound by the load latency)
+      float m[32];
 #pragma unroll
-      for (int q = 0; q < EPDE_MAX_K; q++) {
-        if (q < K) {
-          const float uj = __shfl_sync(0xffffffffu, j < 32 ? u0[q] : u1[q], j & 31);
-          p0[q] = fmaf(m0, uj, p0[q]); p1[q] = fmaf(m1, uj, p1[q]);
+      for (int j = 0; j < 32; j++) if (j < d) m[j] = __ldg(M + (size_t)j * d + c0);
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        if (j < d) {
+#pragma unroll
+          for (int q = 0; q < EPDE_MAX_K; q++)
+            if (q < K) p0[q] = fmaf(m[j], __shfl_sync(0xffffffffu, u0[q], j), p0[q]);
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < d; j++) {
+        const float m0 = __ldg(M + (size_t)j * d + c0);
+        const float m1 = __ldg(M + (size_t)j * d + c1);
+#pragma unroll
+        for (int q = 0; q < EPDE_MAX_K; q++) {
+          if (q < K) {
+            const float uj = __shfl_sync(0xffffffffu, j < 32 ? u0[q] : u1[q], j & 31);
+            p0[q] = fmaf(m0, uj, p0[q]); p1[q] = fmaf(m1, uj, p1[q]);
+          }
         }
       }
     }
@@ -890,7 +904,8 @@ __host__ __device__ inline int fin2_items(int d) { return H + (flat_net_size<H>(
 template <int H>
 __global__ void __launch_bounds__(1024)
 k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
-       const float* __restrict__ params, const float* __restrict__ diag_coeff, float* __restrict__ grad) {
+       const float* __restrict__ params, const float* __restrict__ diag_coeff, float* __restrict__ grad,
+       Peer peer, uint32_t* __restrict__ ticket) {
   static_assert(H <= 32, "one lane per Gamma column");
   __shared__ double sG[H];                       // row o of Gamma
   pdl_wait();                                    // the tensor-core family launches this kernel programmatically (PDL) behind k_pass2_tc
@@ -937,6 +952,22 @@ k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
         const double v = warp_sum(red(e));
         if (lane == 0) g[H * d + rr] = (float)v;
       }
+    }
+  }
+  if (peer.bufs) {
+    // sharded step: the CTA that finishes last all-reduces the whole gradient over NVLink peer memory - no separate
+    // exchange launch.  *ticket is zero at launch (set with the maxima at the start of the step).
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const uint32_t epoch = *peer.epoch + 1u;
+      peer_allreduce_block<float>(peer, epoch, grad, grad, (float*)nullptr, K * fn);
+      __syncthreads();
+      if (threadIdx.x == 0) *peer.epoch = epoch;
     }
   }
 }

@@ -8,6 +8,7 @@
 namespace epde {
 struct Coef;
 struct EigW;
+struct Peer;
 namespace tc {
 
 size_t pack_floats(int d);          // floats of one net's packed weight image
@@ -24,7 +25,8 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 // single-rank step only: reduction of phase 1's partials + the coefficient kernel in one launch (epde_step passes
 // defer_reduce = 1 to partial() and calls this instead of k_reduce_tc / k_coef)
 int reduce_coef(const double* part, int gx, const double* part2, int g2, int k, double* sums, double beta, double alpha,
-                const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st);
+                const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st,
+                const Peer* peer = nullptr);      // peer: sharded step - the sums are all-reduced inside the kernel
 
 // phase 2: k_pass2_tc -> per-CTA gradient images pg[(cta * k + net) * GradLayout.total()], *gx_out = CTAs per net
 int finish(int d, int d_pad, int k, int nsm, int64_t B, const float* xt, const float* wt, const float* pwt,

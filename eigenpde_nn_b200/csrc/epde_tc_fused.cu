@@ -67,9 +67,11 @@ int partial(int d, int d_pad, int k, int nsm, int64_t B, const float* params, co
 }
 
 int reduce_coef(const double* part, int gx, const double* part2, int g2, int k, double* sums, double beta, double alpha,
-                const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st) {
+                const EigW& ew, int sort, double* out, Coef* coef, const float* mx, const float* nrm, cudaStream_t st,
+                const Peer* peer) {
+  const Peer none = {nullptr, 0, 1, nullptr, 0};
   cudaError_t e = launch_pdl(k_reduce_coef_tc, dim3(1), dim3(1024), 0, st, part, gx, part2, g2, k, sums, beta, alpha, ew, sort,
-                             out, coef, mx, nrm);
+                             out, coef, mx, nrm, peer ? *peer : none);
   return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 

@@ -597,12 +597,19 @@ k_reduce_tc(const double* __restrict__ part, int gx, const double* __restrict__ 
 __global__ void __launch_bounds__(1024)
 k_reduce_coef_tc(const double* __restrict__ part, int gx, const double* __restrict__ part2, int g2, int K, double* sums,
                  double beta, double alpha, EigW eigw, int sort, double* __restrict__ out, Coef* __restrict__ coef,
-                 const float* __restrict__ mx, const float* __restrict__ nrm) {
+                 const float* __restrict__ mx, const float* __restrict__ nrm, Peer peer) {
   pdl_trigger();                     // phase 2's CTAs may come in and set up shared / tensor memory while this CTA works
   pdl_wait();                        // k_sums_y (and with it phase 1) complete
   __shared__ double ssums[1 + 2 * EPDE_MAX_K + EPDE_MAX_K * (EPDE_MAX_K + 1) / 2];      // the coefficient part reads the sums from here
   reduce_tc_body(part, gx, part2, g2, K, sums, ssums);
   __syncthreads();
+  if (peer.bufs) {      // sharded step: the sums of all ranks, exchanged over NVLink peer memory by this very CTA
+    const uint32_t epoch = *peer.epoch + 1u;
+    peer_allreduce_block<double>(peer, epoch, ssums, ssums, sums, 1 + 2 * K + K * (K + 1) / 2);
+    __syncthreads();
+    if (threadIdx.x == 0) *peer.epoch = epoch;
+    // the maxima behind phase 2's staging scales stay per rank: every rank scales its own tiles
+  }
   if (threadIdx.x < 32) coef_body<0>(ssums, K, beta, alpha, eigw, sort, out, coef, mx, nrm);
 }
 

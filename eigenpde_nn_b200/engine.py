@@ -141,6 +141,11 @@ class StepEngine:
                 _lib.check(self.lib.epde_step(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
                                               _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), st),
                            "epde_step")
+        elif self._fold_exchange():
+            # both exchanges happen inside the step's own kernels (epde_step_sharded): no exchange launches
+            _lib.check(self.lib.epde_step_sharded(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c,
+                                                  _ptr(ws), C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad),
+                                                  C.byref(self._peer), st), "epde_step_sharded")
         else:
             from .parallel import two_phase_step
 
@@ -164,6 +169,19 @@ class StepEngine:
 
             two_phase_step(partial, finish, self.sums, self.grad, self.pg, self._exchange)
         return self.out, self.grad
+
+    def _fold_exchange(self):
+        """True when the sharded step can run as ONE call with the exchanges inside its kernels: peer exchange available,
+        tensor-core fused family, gradient fits a slot.  EPDE_EXCHANGE_FOLD=0 keeps the separate exchange kernels."""
+        if getattr(self, "_fold", None) is None:
+            import os
+            ex = self._exchange
+            self._fold = bool(ex is not None and self.fused and self.metric is None
+                              and not (self._flags & (_lib.FLAG_FFMA2 | _lib.FLAG_GENERIC))
+                              and ex.fits(self.grad) and os.environ.get("EPDE_EXCHANGE_FOLD", "1") != "0")
+            if self._fold:
+                self._peer = ex.peer_struct()
+        return self._fold
 
     def step(self, idx, params_dev, alpha):
         """Host-facing step: idx is a host int64 array/list (or None for rows 0..B-1 with B = K)."""

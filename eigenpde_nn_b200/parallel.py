@@ -78,6 +78,11 @@ class PeerExchange:
                 print("[eigenpde_nn_b200] peer exchange unavailable:", repr(exc))
             return None
 
+    def peer_struct(self):
+        """The `epde_peer` argument of epde_step_sharded (the exchanges folded into the step's kernels)."""
+        from . import _lib
+        return _lib.EpdePeer(self.hdl.buffer_ptrs_dev, self.rank, self.world, self.epoch_dev.data_ptr(), self.SLOT_BYTES)
+
     def fits(self, t):
         return t.numel() * t.element_size() <= self.SLOT_BYTES
 

@@ -35,8 +35,8 @@
 extern "C" {
 #endif
 
-#define EPDE_ABI_VERSION 3      /* 2: epde_desc.metric, epde_md_align; 3: EPDE_FLAG_FFMA2 replaces epde_set_fused_impl,
-                                   device-side minibatch generator */
+#define EPDE_ABI_VERSION 4      /* 2: epde_desc.metric, epde_md_align; 3: EPDE_FLAG_FFMA2 replaces epde_set_fused_impl,
+                                   device-side minibatch generator; 4: epde_step_sharded, EPDE_FLAG_GENERIC */
 #define EPDE_MAX_LAYERS 8   /* Linear layers per net */
 #define EPDE_MAX_K 8        /* eigenfunctions (nets) */
 
@@ -241,6 +241,26 @@ int epde_train_epilogue64(const epde_desc* desc, double* d_params64, float* d_pa
  * 256 + 2 * world * slot_bytes bytes and zero-filled before the first call.  epoch = 1, 2, 3, ... must advance by one
  * per call on every rank; world <= 32 (the 256-byte flag block holds 2 parities x 32 flags).  In place (src == dst) is allowed.  A peer that never arrives traps after about a minute.
  */
+typedef struct epde_peer {
+  void* const* d_peer_bufs;   /* DEVICE array of `world` pointers to the ranks' symmetric buffers (see below) */
+  int32_t rank, world;        /* world <= 32 */
+  uint32_t* d_epoch;          /* device counter, zero before the first call; shared with epde_peer_allreduce_graph calls */
+  int64_t slot_bytes;         /* per rank and parity; must hold the gradient (4 * epde_param_count bytes) */
+} epde_peer;
+/*
+ * The whole sharded step in one call ("issued from the kernel epilogue by the last-finishing CTA"): as
+ * epde_step on this rank's slice of the global minibatch, with the two exchanges done INSIDE the step's own kernels over
+ * NVLink peer memory - the fp64 sums by the single CTA that reduces the phase-1 partials and computes the coefficients,
+ * the gradient by the last CTA of the final reduction kernel to finish.  No exchange launch, no host involvement; on
+ * return (stream order) d_out_scalars / d_grad hold the results for the union batch, bit-identical on all ranks.
+ * Tensor-core family only: EPDE_ERR_UNSUPPORTED otherwise (use epde_step_partial / allreduce / epde_step_finish).
+ * Replaces src/pytorch_eigen_solver.py:191-233 on each rank of a data-parallel run.
+ */
+int epde_step_sharded(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx, int64_t B,
+                      const float* d_params, const float* d_diag, double beta, double alpha, const double* h_eig_w,
+                      void* d_ws, size_t ws_bytes, double* d_out_scalars, float* d_grad, const epde_peer* peer,
+                      void* stream);
+
 int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
                         int64_t n, int is_f64, int64_t slot_bytes, void* stream);
 /* The same with the epoch kept in device memory (*d_epoch, zero before the first call, advanced by one per call): the

@@ -25,8 +25,12 @@ def main():
     from oracle import closed_form
     import test_gpu_parity as T
     verdict = {"world": world, "cases": []}
-    for (d, k, B, force) in [(50, 3, 40001, "p2p"), (50, 3, 40001, "nccl"), (30, 2, 9001, "p2p"), (50, 6, 20000, "p2p")]:
-        os.environ["EPDE_EXCHANGE"] = force
+    # "p2p": both exchanges inside the step's own kernels (epde_step_sharded); "p2p-unfolded": the separate one-shot exchange
+    # kernel between the phases; "nccl": two NCCL all-reduces
+    for (d, k, B, force) in [(50, 3, 40001, "p2p"), (50, 3, 40001, "p2p-unfolded"), (50, 3, 40001, "nccl"), (30, 2, 9001, "p2p"),
+                             (50, 6, 20000, "p2p"), (2, 2, 777, "p2p")]:
+        os.environ["EPDE_EXCHANGE"] = force.split("-")[0]
+        os.environ["EPDE_EXCHANGE_FOLD"] = "0" if force.endswith("unfolded") else "1"
         c = T._rand_case(11 * d + k, d, k, [20, 20, 20], 50000, B)
         eng = StepEngine(c["X"], c["w"], c["arch"], k, c["act"], c["diag_coeff"], c["beta"], c["eig_w"], device=dev,
                          process_group=dist.group.WORLD)
@@ -48,7 +52,7 @@ def main():
         gathered = [torch.zeros_like(same) for _ in range(world)]
         dist.all_gather(gathered, same)
         identical = all(torch.equal(gathered[0], t) for t in gathered)      # every rank holds bit-identical results
-        used = "peer" if eng._exchange is not None else "nccl"
+        used = ("peer-folded" if eng._fold_exchange() else "peer") if eng._exchange is not None else "nccl"
         verdict["cases"].append(dict(d=d, k=k, B=B, requested=force, exchange=used, worst_vs_oracle=float(worst),
                                      grad_vs_single_rank=rel, identical_on_all_ranks=bool(identical)))
         assert rel <= 1e-5 and identical, verdict["cases"][-1]

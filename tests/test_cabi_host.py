@@ -26,7 +26,7 @@ def test_exports_match_header(L):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.epde_abi_version() == _lib.ABI_VERSION == 3
+    assert L.epde_abi_version() == _lib.ABI_VERSION == 4
     assert L.epde_error_string(0) == b"ok"
     assert b"workspace" in L.epde_error_string(-4)
 
