@@ -322,8 +322,13 @@ struct GenericPlan {
       *Zb[EPDE_MAX_LAYERS + 1];
   double *part, *gacc; Coef* coef;
   float* cpart; size_t cpart_floats;                      // split-K partial tiles of the tcgen05 GEMM
+  // Stash (SURVEY H2 option C for this family): phase 1 keeps Z, A, G, U, U0 of every (chunk, net) so that phase 2 does
+  // not repeat the forward + Jacobian chain (2 of its 6 GEMM sweeps and two element-wise kernels per layer).  One set is
+  // stash_set floats; used while the whole stash stays below kGenericStashLimit, else phase 2 recomputes as before.
+  float* stash; size_t stash_set; int64_t nchunks;
   size_t total;
 };
+constexpr size_t kGenericStashLimit = (size_t)40 << 30;
 
 inline size_t g_align(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -364,8 +369,30 @@ inline GenericPlan generic_plan(const epde_desc* D, int64_t B, void* base) {
     P.U[l] = (float*)take((size_t)bc * P.n[l] * 4);
     P.Zb[l] = (float*)take((size_t)bc * P.n[l] * 4);
   }
+  P.nchunks = (B + bc - 1) / bc;
+  P.stash_set = (size_t)bc * D->d_pad;
+  for (int l = 1; l <= P.L; l++) P.stash_set += (size_t)4 * bc * P.n[l];
+  P.stash_set = (P.stash_set + 63) / 64 * 64;
+  const size_t stash_bytes = P.stash_set * 4 * (size_t)P.nchunks * D->k;
+  P.stash = (stash_bytes <= kGenericStashLimit) ? (float*)take(stash_bytes) : nullptr;
+  if (stash_bytes > kGenericStashLimit) P.stash_set = 0;
   P.total = off;
   return P;
+}
+// the plan with Z, A, G, U, U0 pointing into the stash set of (chunk, net); unchanged without a stash
+inline GenericPlan stash_view(const GenericPlan& P, int64_t chunk, int net, int k, int d_pad) {
+  if (!P.stash_set) return P;
+  GenericPlan Q = P;
+  float* p = P.stash ? P.stash + ((size_t)chunk * k + net) * P.stash_set : nullptr;
+  const size_t bc = (size_t)P.Bc;
+  Q.U0 = p; if (p) p += bc * d_pad;
+  for (int l = 1; l <= P.L; l++) {
+    Q.Z[l] = p; if (p) p += bc * P.n[l];
+    Q.A[l] = p; if (p) p += bc * P.n[l];
+    Q.G[l] = p; if (p) p += bc * P.n[l];
+    Q.U[l] = p; if (p) p += bc * P.n[l];
+  }
+  return Q;
 }
 
 inline int generic_workspace_bytes(const epde_desc* D, int64_t B, size_t* out) {
@@ -486,8 +513,9 @@ inline int generic_partial(const epde_desc* D, const float* X, const float* w, c
     g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P.Xc);
     for (int net = 0; net < D->k; net++) {
       const NetParams np = net_params(P, params, net);
-      generic_fwd_jac(D, P, np, Bc, true, st);
-      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, P.Z[P.L], b0, D->k, net, P.ybuf, P.ebuf, D->metric, idx);
+      const GenericPlan Q = stash_view(P, b0 / P.Bc, net, D->k, D->d_pad);      // phase 2 finds Z, A, G, U, U0 here
+      generic_fwd_jac(D, Q, np, Bc, true, st);
+      g_energy<<<g_blocks(Bc), 256, 0, st>>>(Bc, D->d, D->d_pad, Q.U0, diag, Q.Z[Q.L], b0, D->k, net, P.ybuf, P.ebuf, D->metric, idx);
     }
   }
   int nb = (int)((B + 255) / 256); if (nb > 256) nb = 256;
@@ -500,20 +528,21 @@ inline int generic_partial(const epde_desc* D, const float* X, const float* w, c
 inline int generic_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                           const float* params, const float* diag, double beta, double alpha, const EigW& ew,
                           const double* sums, void* ws, double* out, float* grad, cudaStream_t st) {
-  GenericPlan P = generic_plan(D, B, ws);
-  const int L = P.L, act = D->act_id;
-  const TcCtx tc{P.cpart, P.cpart_floats};
-  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, P.coef);
-  int64_t per = 0; for (int l = 1; l <= L; l++) per += (int64_t)P.n[l] * P.n[l - 1] + P.n[l];
-  g_zero_d<<<g_blocks(per * D->k), 256, 0, st>>>(per * D->k, P.gacc);
-  generic_pad_weights(D, P, params, st);
-  for (int64_t b0 = 0; b0 < B; b0 += P.Bc) {
-    const int Bc = (int)((B - b0 < P.Bc) ? B - b0 : P.Bc);
-    g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P.Xc);
-    g_fill<<<g_blocks(Bc), 256, 0, st>>>(Bc, 1.0f, P.ones);
+  const GenericPlan P0 = generic_plan(D, B, ws);
+  const int L = P0.L, act = D->act_id;
+  const TcCtx tc{P0.cpart, P0.cpart_floats};
+  k_coef<<<1, 32, 0, st>>>(sums, D->k, beta, alpha, ew, (D->flags & EPDE_FLAG_SORT) ? 1 : 0, out, P0.coef);
+  int64_t per = 0; for (int l = 1; l <= L; l++) per += (int64_t)P0.n[l] * P0.n[l - 1] + P0.n[l];
+  g_zero_d<<<g_blocks(per * D->k), 256, 0, st>>>(per * D->k, P0.gacc);
+  generic_pad_weights(D, P0, params, st);
+  for (int64_t b0 = 0; b0 < B; b0 += P0.Bc) {
+    const int Bc = (int)((B - b0 < P0.Bc) ? B - b0 : P0.Bc);
+    g_gather<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(X, idx, b0, Bc, D->d_pad, P0.Xc);
+    g_fill<<<g_blocks(Bc), 256, 0, st>>>(Bc, 1.0f, P0.ones);
     for (int net = 0; net < D->k; net++) {
-      const NetParams np = net_params(P, params, net);
-      generic_fwd_jac(D, P, np, Bc, true, st);
+      const NetParams np = net_params(P0, params, net);
+      const GenericPlan P = stash_view(P0, b0 / P0.Bc, net, D->k, D->d_pad);
+      if (!P0.stash_set) generic_fwd_jac(D, P, np, Bc, true, st);      // no stash: recompute forward + Jacobian chain
       // ---- first reverse sweep (energy term), l = 1..L
       g_seed<<<g_blocks((int64_t)Bc * D->d_pad), 256, 0, st>>>(Bc, D->d, D->d_pad, P.U0, diag, w, idx, b0, P.coef, net, P.Ub, D->metric);
       for (int l = 1; l <= L; l++) {
@@ -545,7 +574,7 @@ inline int generic_finish(const epde_desc* D, const float* X, const float* w, co
       }
     }
   }
-  g_to_float<<<g_blocks(per * D->k), 256, 0, st>>>(per * D->k, P.gacc, grad);
+  g_to_float<<<g_blocks(per * D->k), 256, 0, st>>>(per * D->k, P0.gacc, grad);
   return (int)cudaGetLastError();
 }
 

@@ -299,7 +299,8 @@ class eigen_solver():
         print('\n[Info] Time spent for loading data: %.2f Sec' % (time.process_time() - self.start_time))
         print('[Info] Total number of parameters in networks: %d' % tot_num_parameters)
         print("[Info]  NN architecture:", self.arch_list)
-        print("[Info]  B200 step: %s kernels" % ("fused FFMA2" if self.engine.fused else "generic layer-wise"))
+        print("[Info]  B200 step: %s kernels" % (("fused FFMA2 (per-row metric)" if self.engine.metric is not None else "fused tcgen05")
+                                                 if self.engine.fused else "generic layer-wise"))
 
         self.train()
 
