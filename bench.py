@@ -14,7 +14,7 @@ Prints ONE JSON line (rank 0).  `value` = samples/s with the index batch already
 MT19937 stream on the device (bit-exact with random.choices, src/data_set.py:67; generation inside the timed
 region, one step ahead on a second stream), uploads the parameters from pinned host memory and reads the
 gradient + scalars back.  With N > 1 a pre-timing self-check compares the N-rank step with a single-rank
-step on the union batch (`parity`).  `extra` (N = 1 only) carries BASELINE configs 4 and 5.
+step on the union batch (`parity`).  `extra` (N = 1 only) carries BASELINE configs 4 and 5 and config 3 in MD mode.
 """
 from __future__ import annotations
 
@@ -212,6 +212,35 @@ def extra_workloads(dev, X, w):
                                  "frac_tf32x3_ceiling": flopw * Bw / (ms * 1e-3) / 1e12 / (TENSOR_PEAK_TFLOPS / 6.0),
                                  "fused": bool(eng.fused), "loss": loss}
     del eng
+    torch.cuda.empty_cache()
+    # BASELINE config 3 WITH the alignment layer: 30-D (10 atoms), k = 2, B = 10000 of K = 1e5 frames, NAMD-style
+    # weights; epde_md_align once per data set, then the step with the per-row metric on the fused FFMA2 kernels + k_metric
+    from eigenpde_nn_b200.engine import md_align
+    rng = np.random.default_rng(0)
+    Km, dm, Bm = 100000, 30, 10000
+    Xm = (1.5 * rng.standard_normal((1, dm)) + np.sqrt(0.1) * rng.standard_normal((Km, dm))).astype(np.float32)
+    wm = np.exp(2.0 * rng.standard_normal(Km)).astype(np.float32); wm /= wm.mean()
+    ri = [0, 2, 5, 7, 8]
+    ref = Xm[0].reshape(-1, 3)[ri].astype(np.float64); ref -= ref.mean(0, keepdims=True)
+    beta_md = 1.0 / (0.001987191 * 300.0)
+    diag = np.full(dm, 1e-5 * 1e7 * beta_md)
+    Xa, Mx = md_align(Xm, ref, ri, diag, device=dev)
+    eng = StepEngine(Xa, torch.from_numpy(wm), [dm, 20, 20, 20, 1], 2, "Tanh", diag, beta_md, [1.0, 0.8], device=dev, metric=Mx)
+    idx = torch.randint(0, Km, (Bm,), generator=torch.Generator(device=dev).manual_seed(3), device=dev, dtype=torch.int64)
+    params = (0.5 * torch.randn(eng.n_params, generator=torch.Generator().manual_seed(9))).to(dev)
+    for _ in range(3):
+        eng.step_device(idx, Bm, params, ALPHA)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        eng.step_device(idx, Bm, params, ALPHA)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out["cfg3_md_30d_k2_aligned"] = {"workload": "30-D MD frames through the alignment layer (per-row metric), k=2, B=10000",
+                                     "batch": Bm, "samples_per_s": Bm / (ms * 1e-3), "ms_per_step": ms, "fused": bool(eng.fused),
+                                     "loss": float(eng.out[0])}
+    del eng, Xa, Mx
     torch.cuda.empty_cache()
     return out
 
