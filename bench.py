@@ -390,18 +390,18 @@ def main():
     t_p1 /= nphase; t_p2 /= nphase
 
     # ---- end to end through the host-facing API --------------------------------------------
-    out_pin = torch.empty(eng.out.numel(), dtype=torch.float64).pin_memory()
-    grad_pin = torch.empty(eng.n_params, dtype=torch.float32).pin_memory()
+    res_pin = torch.empty(eng.result.numel(), dtype=torch.uint8).pin_memory()      # scalars (fp64) + gradient (fp32), one copy
+    out_pin = res_pin[:8 * eng.out.numel()].view(torch.float64)
     par_stage = torch.empty_like(params)
     ahead = DrawAhead(mb, world * B, lo=rank * B, n=B).start()          # step i+1's indices are generated behind step i
 
     def e2e_step(i):
-        idx_stage = ahead.take()                                       # fresh draw from the MT19937 stream (device, side stream)
+        idx_stage = ahead.take(defer=True)                             # fresh draw from the MT19937 stream (device, side stream)
         par_stage.copy_(params_h, non_blocking=True)                   # H2D: current parameters
-        o, gr = eng.step_device(idx_stage, B, par_stage, ALPHA)
+        eng.step_device(idx_stage, B, par_stage, ALPHA)
         ahead.done_with(idx_stage)
-        out_pin.copy_(o, non_blocking=True)                            # D2H: loss / eigenvalues / penalty
-        grad_pin.copy_(gr, non_blocking=True)                          # D2H: gradient for the host optimiser
+        res_pin.copy_(eng.result, non_blocking=True)                   # D2H: loss / eigenvalues / penalty + gradient for the host optimiser
+        ahead.enqueue_next()                                           # the next step's draw, behind this step's kernels
         torch.cuda.current_stream().synchronize()                      # update_step returns host values (:236)
         return float(out_pin[0])
 

@@ -23,7 +23,8 @@ ABI_VERSION = 4
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
            "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_step_sharded", "epde_forward",
-           "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_mt_jump_poly", "epde_mt_jump_device",
+           "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_minibatch_indices_device_split", "epde_mt_jump_poly",
+           "epde_mt_jump_device",
            "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
            "epde_eig_stats_accumulate", "epde_md_align", "epde_train_epilogue", "epde_train_epilogue64", "epde_peer_allreduce", "epde_peer_allreduce_graph"]
 
@@ -69,6 +70,7 @@ def lib():
         L.epde_forward.argtypes = [dp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
         L.epde_minibatch_indices.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, vp]
         L.epde_minibatch_indices_device.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]
+        L.epde_minibatch_indices_device_split.argtypes = [vp, C.c_int32, i64, i64, i64, vp, vp, vp]
         L.epde_mt_jump_poly.argtypes = [i64, vp]
         L.epde_mt_jump_device.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
         L.epde_mt_seed.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_int32)]

@@ -453,8 +453,21 @@ int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total,
   if (K < 1 || B_total < 0 || B_total >= (1ll << 30) || out_lo < 0 || out_n < 0 || out_lo + out_n > B_total) return EPDE_ERR_ARG;
   if (((uintptr_t)d_raw & 7) || ((uintptr_t)d_state & 3)) return EPDE_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, (int)(2 * B_total), d_raw);
+  k_mt_generate<<<1, MT_THREADS, 0, st>>>(d_state, (int)(2 * B_total), d_raw, (int)(2 * B_total));
   if (out_n > 0) k_mt_to_idx<<<(unsigned)((out_n + 255) / 256), 256, 0, st>>>(d_raw, K, out_lo, out_n, d_idx);
+  return (int)cudaGetLastError();
+}
+
+int epde_minibatch_indices_device_split(uint32_t* d_states, int32_t parts, int64_t K, int64_t n_sub, int64_t n_total,
+                                        uint32_t* d_raw, int64_t* d_idx, void* stream) {
+  if (!d_states || !d_raw || !d_idx) return EPDE_ERR_NULL;
+  if (K < 1 || parts < 1 || parts > 64 || n_sub < 1 || n_total < 1 || n_total >= (1ll << 30) ||
+      (int64_t)(parts - 1) * n_sub >= n_total || (int64_t)parts * n_sub < n_total)
+    return EPDE_ERR_ARG;
+  if (((uintptr_t)d_raw & 7) || ((uintptr_t)d_states & 3)) return EPDE_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_mt_generate<<<parts, MT_THREADS, 0, st>>>(d_states, (int)(2 * n_sub), d_raw, (int)(2 * n_total));
+  k_mt_to_idx<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(d_raw, K, 0, n_total, d_idx);
   return (int)cudaGetLastError();
 }
 

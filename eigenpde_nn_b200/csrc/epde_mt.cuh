@@ -33,10 +33,15 @@ __host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // state[0..623] = mt, state[624] = pos (0..624).  Consumes W = 2 * B words (W < 2^31) starting at position pos of the
 // current block and writes them (untempered) to raw[0..W).  One CTA of MT_THREADS threads; 32-bit index arithmetic and
 // warp-uniform branches only (the CTA is issue-bound: 20 warps on one SM).
+// gridDim.x > 1: CTA q continues the generator state + 625 q (a state jumped ahead to word q Wsub of the slice,
+// epde_mt_jump_device) for the words [q Wsub, min((q + 1) Wsub, Wtot)) - the sequential recurrence runs on several SMs at once.
 static __global__ void __launch_bounds__(MT_THREADS, 1)
-k_mt_generate(uint32_t* __restrict__ state, int W, uint32_t* __restrict__ raw) {
+k_mt_generate(uint32_t* __restrict__ state, int Wsub, uint32_t* __restrict__ raw, int Wtot) {
   __shared__ uint32_t buf[MT_N + MT_STEP * MT_CHUNK];
   const int tid = threadIdx.x;
+  state += (size_t)blockIdx.x * (MT_N + 1);
+  raw += (size_t)blockIdx.x * Wsub;
+  const int W = min(Wsub, Wtot - (int)blockIdx.x * Wsub);
   const int p0 = (int)state[MT_N];
   for (int i = tid; i < MT_N; i += MT_THREADS) buf[i] = state[i];
   __syncthreads();

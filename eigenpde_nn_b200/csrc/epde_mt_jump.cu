@@ -151,11 +151,15 @@ k_mt_window(const uint32_t* __restrict__ state, uint32_t* __restrict__ win) {
   for (int i = tid; i < 20560; i += MT_THREADS) win[i] = wbuf[t + i];
 }
 
-// out[m] = XOR_{i : g_i = 1} win[i + m], m = 0..623; out[624] = 0 (position).  One warp per output word pair ...
+// out[m] = XOR_{i : g_i = 1} win[i + m], m = 0..623; out[624] = 0 (position).  One warp per output word; blockIdx.y = which
+// polynomial / output state: all jumps of a step run in ONE launch (they are latency-bound chains of dependent loads).
+struct MtOuts { uint32_t* p[32]; };
 __global__ void __launch_bounds__(256)
-k_mt_apply(const uint32_t* __restrict__ win, const uint32_t* __restrict__ poly, uint32_t* __restrict__ out) {
+k_mt_apply(const uint32_t* __restrict__ win, const uint32_t* __restrict__ polys, MtOuts outs) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int m = blockIdx.x * 8 + wid;                 // 78 CTAs x 8 warps = 624 output words
+  const uint32_t* poly = polys + (size_t)blockIdx.y * MT_N;
+  uint32_t* out = outs.p[blockIdx.y];
   uint32_t acc = 0;
   for (int w = lane; w < MT_N; w += 32) {             // lane-strided words of the polynomial
     uint32_t g = __ldg(poly + w);
@@ -181,16 +185,19 @@ extern "C" {
 int epde_mt_jump_device(const uint32_t* d_state_in, const uint32_t* d_polys, int32_t n_polys, uint32_t* const* h_state_out,
                         uint32_t* d_window, void* stream) {
   if (!d_state_in || !d_polys || !h_state_out || !d_window) return EPDE_ERR_NULL;
-  if (n_polys < 1 || n_polys > 8) return EPDE_ERR_ARG;
+  if (n_polys < 1 || n_polys > 32) return EPDE_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)MT_WIN_MAX * 4;
   cudaError_t e = cudaFuncSetAttribute(epde::k_mt_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  epde::k_mt_window<<<1, epde::MT_THREADS, smem, st>>>(d_state_in, d_window);
+  epde::MtOuts outs;
+  for (int k = 0; k < 32; k++) outs.p[k] = nullptr;
   for (int k = 0; k < n_polys; k++) {
     if (!h_state_out[k]) return EPDE_ERR_NULL;
-    epde::k_mt_apply<<<78, 256, 0, st>>>(d_window, d_polys + (size_t)k * 624, h_state_out[k]);
+    outs.p[k] = h_state_out[k];
   }
+  epde::k_mt_window<<<1, epde::MT_THREADS, smem, st>>>(d_state_in, d_window);
+  epde::k_mt_apply<<<dim3(78, n_polys), 256, 0, st>>>(d_window, d_polys, outs);
   return (int)cudaGetLastError();
 }
 

@@ -75,8 +75,11 @@ class StepEngine:
                 self.w = torch.as_tensor(np.asarray(weights), dtype=torch.float32).to(self.device).contiguous()
             self.diag = torch.as_tensor(np.asarray(diag_coeff), dtype=torch.float32).to(self.device).contiguous()
             self.sums = torch.zeros(self.n_sums, dtype=torch.float64, device=self.device)
-            self.out = torch.zeros(4 + 4 * self.k, dtype=torch.float64, device=self.device)
-            self.grad = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+            # out (fp64 scalars) and grad (fp32) are views of ONE buffer: a single device -> host copy returns both
+            nout = 4 + 4 * self.k
+            self.result = torch.zeros(8 * nout + 4 * self.n_params, dtype=torch.uint8, device=self.device)
+            self.out = self.result[:8 * nout].view(torch.float64)
+            self.grad = self.result[8 * nout:].view(torch.float32)
         self._ws = None
         self._ws_B = 0
         self.ws_generation = 0          # bumped whenever the step workspace is re-allocated (captured graphs hold its address)
@@ -244,7 +247,8 @@ class DeviceMinibatch:
     continued ON THE DEVICE: the MT19937 state of Python's `random` is uploaded once (`seed_from_python`), every `draw`
     is two kernels of the library (`epde_minibatch_indices_device`) with no host involvement, and `sync_to_python` hands
     the advanced state back to `random.setstate` -- after it, `random` is exactly where the reference would have left it.
-    With world > 1 every rank advances the whole global stream and keeps its own contiguous slice."""
+    With world > 1 every rank jumps ahead to its own contiguous slice of the global stream; large draws are split over
+    several CTAs by the same jump-ahead (`_draw_slice`)."""
 
     def __init__(self, K, device, lib=None):
         self.lib = lib if lib is not None else _lib.lib()
@@ -285,28 +289,38 @@ class DeviceMinibatch:
             self._polys[J] = t
         return t
 
+    SPLIT_MIN = 1 << 18          # draws from which a slice is generated by several CTAs at once
+    SPLIT_PARTS = 8
+
     def _draw_slice(self, B_total, out, lo, n):
-        """Sharded draw: jump to this rank's slice (2 * lo words) and to the next step (2 * B_total words) from one window of
-        the base state, then generate only the 2 * n words of the slice (csrc/epde_mt_jump.cu)."""
+        """Draw by jump-ahead: from ONE window of the base state, jump to the next step (2 * B_total words) and to the start
+        of this rank's slice (2 * lo words) - for a large slice to the starts of its SPLIT_PARTS parts, which are then
+        generated by as many CTAs at once (the recurrence is sequential per generator: 1.25 G draws/s on one SM).  Only the
+        2 * n words of the slice are generated (csrc/epde_mt_jump.cu, csrc/epde_mt.cuh)."""
+        parts = self.SPLIT_PARTS if n >= self.SPLIT_MIN else 1
+        n_sub = (n + parts - 1) // parts if n > 0 else 1
+        while parts > 1 and (parts - 1) * n_sub >= n:
+            parts -= 1
+        key = (B_total, lo, n, parts)
         if self._jump is None:
+            self._jump = {}
+        J = self._jump.get(key)
+        if J is None:      # buffers are kept per (batch, slice): a captured CUDA graph may hold their addresses
             dev = self.device
-            self._jump = dict(slice=torch.zeros(625, dtype=torch.int32, device=dev), nxt=torch.zeros(625, dtype=torch.int32, device=dev),
-                              win=torch.empty(20560, dtype=torch.int32, device=dev), key=None, polys=None)
-        J = self._jump
-        if J["key"] != (B_total, lo):
-            J["polys"] = torch.cat([self._poly(2 * lo), self._poly(2 * B_total)]).contiguous()
-            J["key"] = (B_total, lo)
-            J["outs"] = (C.c_void_p * 2)(J["slice"].data_ptr(), J["nxt"].data_ptr())
+            states = torch.zeros((parts + 1, 625), dtype=torch.int32, device=dev)      # part generators, then the next base state
+            polys = torch.cat([self._poly(2 * (lo + q * n_sub)) for q in range(parts)] + [self._poly(2 * B_total)]).contiguous()
+            outs = (C.c_void_p * (parts + 1))(*[states[q].data_ptr() for q in range(parts + 1)])
+            J = self._jump[key] = dict(states=states, polys=polys, outs=outs, win=torch.empty(20560, dtype=torch.int32, device=dev))
         if self._raw is None or self._raw.numel() < 2 * n:
             self._raw = torch.empty(max(2 * n, 2), dtype=torch.int32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(self.lib.epde_mt_jump_device(_ptr(self.state), _ptr(J["polys"]), 2, J["outs"], _ptr(J["win"]), st),
+        _lib.check(self.lib.epde_mt_jump_device(_ptr(self.state), _ptr(J["polys"]), parts + 1, J["outs"], _ptr(J["win"]), st),
                    "epde_mt_jump_device")
         if n > 0:
-            _lib.check(self.lib.epde_minibatch_indices_device(_ptr(J["slice"]), C.c_int64(self.K), C.c_int64(n), C.c_int64(0),
-                                                              C.c_int64(n), _ptr(self._raw), _ptr(out), st),
-                       "epde_minibatch_indices_device")
-        self.state.copy_(J["nxt"])                  # same address every step: the draw can sit inside a replayed CUDA graph
+            _lib.check(self.lib.epde_minibatch_indices_device_split(_ptr(J["states"]), parts, C.c_int64(self.K), C.c_int64(n_sub),
+                                                                    C.c_int64(n), _ptr(self._raw), _ptr(out), st),
+                       "epde_minibatch_indices_device_split")
+        self.state.copy_(J["states"][parts])        # same address every step: the draw can sit inside a replayed CUDA graph
         return out
 
     def draw(self, B_total, out=None, lo=0, n=None):
@@ -319,7 +333,8 @@ class DeviceMinibatch:
         if B_total == 0:
             return out
         import os
-        if (lo != 0 or n != B_total) and os.environ.get("EPDE_MT_JUMP", "1") != "0":
+        if (lo != 0 or n != B_total) and os.environ.get("EPDE_MT_JUMP", "1") != "0":      # (a whole-stream draw stays sequential:
+            # it leaves the generator exactly as CPython would show it, block and position)
             return self._draw_slice(B_total, out, lo, n)
         if self._raw is None or self._raw.numel() < 2 * B_total:
             self._raw = torch.empty(2 * B_total, dtype=torch.int32, device=self.device)
@@ -361,12 +376,18 @@ class DrawAhead:
             self.ready[b].record(self.stream)
         self.head += 1
 
-    def take(self):
-        """Indices of the current step; the draw of the following step starts right away on the side stream."""
+    def take(self, defer=False):
+        """Indices of the current step; the draw of the following step starts right away on the side stream - or, with
+        defer=True, when the caller says so (`enqueue_next()`, after it has launched the step: enqueueing the draw costs
+        host time that would otherwise sit between the previous step's results and this step's first kernel)."""
         b = self.tail & 1
         torch.cuda.current_stream(self.mb.device).wait_event(self.ready[b])
-        self._enqueue()
+        if not defer:
+            self._enqueue()
         return self.buf[b]
+
+    def enqueue_next(self):
+        self._enqueue()
 
     def done_with(self, idx):
         self.free[self.tail & 1].record(torch.cuda.current_stream(self.mb.device))

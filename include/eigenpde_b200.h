@@ -179,12 +179,21 @@ int epde_minibatch_indices(uint32_t* h_mt, int32_t* h_pos, int64_t K, int64_t B,
  */
 int epde_minibatch_indices_device(uint32_t* d_state, int64_t K, int64_t B_total, int64_t out_lo, int64_t out_n,
                                   uint32_t* d_raw, int64_t* d_idx, void* stream);
+/*
+ * The sequential recurrence on several SMs at once: d_states holds `parts` generators of 625 uint32 each, generator q
+ * positioned (epde_mt_jump_device) at draw q * n_sub of a run of n_total draws; CTA q generates the draws
+ * [q n_sub, min((q + 1) n_sub, n_total)) and all n_total indices go to d_idx.  (parts - 1) * n_sub < n_total <= parts * n_sub.
+ * d_raw: scratch of 2 * n_total uint32.  The states are left advanced past their own parts (of no further use: the caller
+ * takes the next step's generator from another jump).  Same stream (src/data_set.py:31,67,77), bit-exact.
+ */
+int epde_minibatch_indices_device_split(uint32_t* d_states, int32_t parts, int64_t K, int64_t n_sub, int64_t n_total,
+                                        uint32_t* d_raw, int64_t* d_idx, void* stream);
 
 /*
  * Jump-ahead for the sharded stream (csrc/epde_mt_jump.cu).  MT19937 is linear over GF(2): the generator J words ahead is a
  * fixed XOR-combination, given by g_J(x) = x^J mod (characteristic polynomial), of the next 20 560 words.
  *   epde_mt_jump_poly: host, g_J as 624 uint32 (about 0.2 s; depends only on J -- compute once per slice offset / batch size).
- *   epde_mt_jump_device: from the generator d_state_in (625 uint32) produce, for each of the n_polys <= 8 polynomials in
+ *   epde_mt_jump_device: from the generator d_state_in (625 uint32) produce, for each of the n_polys <= 32 polynomials in
  *     d_polys (n_polys x 624 uint32, device), the generator advanced by that jump into h_state_out[k] (host array of device
  *     pointers, 625 uint32 each: the 624-word window at the target position, position word 0 -- the same stream position in
  *     a different representation than CPython's (block, position) pair).  d_window: scratch of 20 560 uint32.
