@@ -66,7 +66,7 @@ int num_sums(int k) { return 1 + 2 * k + k * (k + 1) / 2; }
 struct FusedWs {
   float* pw; float* ybuf; double* part; Coef* coef; float* pg; float* xt; float* wt; float* pwt; double* part2;
   float* mx; float* nrm;      // bounds for the fp16 gradient rounds (epde_coef.cuh); mx is followed by k_fin2's ticket word
-  float* stash;               // phase-1 intermediates of the tensor-core family (480 B per sample and net)
+  float* stash;               // phase-1 intermediates of the tensor-core family (400 B per sample and net)
   float* U; double* epart;    // per-row metric: u0 -> p of every net [k][tiles][d][256], k_metric's partial energy sums
   size_t total;
 };

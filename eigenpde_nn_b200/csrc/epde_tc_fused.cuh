@@ -321,9 +321,11 @@ __device__ __forceinline__ void store_vec24(uint32_t ahi_t, uint32_t alo_t, cons
 //   part[(net * gridDim.x + blockIdx.x) * 2 + {0,1}] = sum w y, sum w e  (fp64);   ybuf[n][k]
 // ---------------------------------------------------------------------------------------------
 // Per-sample intermediates phase 1 hands to phase 2 (SURVEY H2 option C: stash instead of recompute):
-//   stash[tile128][net][vector][feature][128 samples], vectors 0 a1, 1 a2, 2 a3, 3 g2, 4 g1, 5 t = K g1   (fp32)
-// 480 B per sample and net, written and read exactly once with coalesced 128-byte rows (streaming: far larger than L2).
-constexpr int ST_VECS = 6;
+//   stash[tile128][net][vector][feature][128 samples], vectors 0 a1, 1 a2, 2 a3, 3 g2, 4 g1   (fp32)
+// 400 B per sample and net, written and read exactly once with coalesced 128-byte rows (streaming: far larger than L2).
+// (t = K g1 was a sixth vector: phase 1 is bound by the stash write, and phase 2 recomputes t with one mat-vec that runs
+//  behind the flush of the previous tile's accumulators.)
+constexpr int ST_VECS = 5;
 constexpr size_t ST_TILE = (size_t)ST_VECS * TH * 128;          // floats per tile and net
 __device__ __forceinline__ void stash_st(float* p, int vec, const float* v) {
 #pragma unroll
@@ -490,7 +492,6 @@ k_pass1_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
 #pragma unroll
     for (int i = 0; i < H; i += 2) { e0 = fmaf(v[i], z[i], e0); e1 = fmaf(v[i + 1], z[i + 1], e1); mt = fmaxf(mt, fmaxf(fabsf(z[i]), fabsf(z[i + 1]))); }
     const float e = e0 + e1;
-    stash_st(sp, 5, z);
     my = fmaxf(my, fabsf(y));
 #undef EPDE_TC_STAGE
 #undef EPDE_TC_MV

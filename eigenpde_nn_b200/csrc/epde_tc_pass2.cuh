@@ -317,16 +317,25 @@ k_pass2_tc(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B
     float z[H], v[TKH], a1[H], a2[H], a3[H], g1[H], g2[H], ze1[H], ze2[H];
     // (requesting z, a1, g1 one tile ahead - across the loop back-edge - was measured and is SLOWER: 0.81 vs 0.77 ms;
     //  60 more live registers through the flush)
-    stash_ld(sp, 5, z); stash_ld(sp, 0, a1); stash_ld(sp, 4, g1);
-    if (t + tstep < nt128) {      // the next tile's stash rows (120 rows of 512 B) towards L2: 480 lines, 4 per thread
+    stash_ld(sp, 4, g1); stash_ld(sp, 0, a1);
+    if (t + tstep < nt128) {      // the next tile's stash rows (100 rows of 512 B) towards L2: 400 lines, up to 4 per thread
       const char* nx = reinterpret_cast<const char*>(stash + ((size_t)(t + tstep) * K + net) * ST_TILE);
 #pragma unroll
-      for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)(q * 128 + sn) << 7)));
+      for (int q = 0; q < 4; q++)
+        if (q * 128 + sn < (int)(ST_TILE * 4 / 128)) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + ((size_t)(q * 128 + sn) << 7)));
     }
+    // ---- S5: t = K g1 (not stashed: phase 1 is bound by the stash write); the mat-vec runs while the previous tile's
+    //      accumulators are flushed
+    v[20] = 0.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;       // no bias rows in the reverse sweeps
+#pragma unroll
+    for (int i = 0; i < H; i++) v[i] = g1[i];
+    store_vec24(tl + ahi, tl + alo, v);
+    EPDE_P2_MV_REQ(4)                                   // K g1
     if (window_start && lt > 0) { round_wait(); flush1(); flush2(); flush3(); TC_ADD(6); }
     stash_ld(sp, 1, a2); stash_ld(sp, 3, g2); stash_ld(sp, 2, a3);
-    v[20] = 0.f; v[21] = 0.f; v[22] = 0.f; v[23] = 0.f;       // no bias rows in the reverse sweeps
     tm_st16(pkA, a1); tm_st4(pkA + 16, a1 + 16);              // a1 is parked in TMEM until S9 / S10
+    EPDE_P2_WAIT()
+    tm_ld20(tl + dcol, z);                                    // t
     TC_ADD(4);
     // ---- S6: gbar1 = 2 ebar K g1, ubar1 -> gbar2 = W2 ubar1 --------------------------------------------
     float ub1[H];
