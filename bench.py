@@ -353,15 +353,22 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # every step announces the next step's (already drawn) index batch: its rows are gathered on a second stream while the
+    # step computes (engine._step_ahead; EPDE_GATHER_AHEAD=0 switches the look-ahead off).  The loops run on the engine's
+    # compute stream (the high-priority stream of the look-ahead scheme) so that no hand-over events are needed per step.
+    cs = eng.compute_stream()
+    if cs is not None:
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        torch.cuda.set_stream(cs)
     for i in range(W):
-        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA)
+        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA, next_idx=idx_dev[(i + 1) % nbatch])
     barrier()
     sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(args.steps):
-        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA)
+        eng.step_device(idx_dev[i % nbatch], B, params, ALPHA, next_idx=idx_dev[(i + 1) % nbatch])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -393,15 +400,22 @@ def main():
     res_pin = torch.empty(eng.result.numel(), dtype=torch.uint8).pin_memory()      # scalars (fp64) + gradient (fp32), one copy
     out_pin = res_pin[:8 * eng.out.numel()].view(torch.float64)
     par_stage = torch.empty_like(params)
-    ahead = DrawAhead(mb, world * B, lo=rank * B, n=B).start()          # step i+1's indices are generated behind step i
+    from eigenpde_nn_b200.engine import LATER
+    use_ahead = eng._ahead_ok()
+    # the draws of the next TWO steps are kept in flight: step i + 1's indices are complete while step i runs (its rows are
+    # gathered beside step i's phase 2), step i + 2's are being generated
+    ahead = DrawAhead(mb, world * B, lo=rank * B, n=B, depth=2 if use_ahead else 1).start()
 
     def e2e_step(i):
         idx_stage = ahead.take(defer=True)                             # fresh draw from the MT19937 stream (device, side stream)
         par_stage.copy_(params_h, non_blocking=True)                   # H2D: current parameters
-        eng.step_device(idx_stage, B, par_stage, ALPHA)
+        eng.step_device(idx_stage, B, par_stage, ALPHA, next_idx=LATER if use_ahead else None)
+        if use_ahead:
+            nxt, drawn = ahead.peek(1)
+            eng.gather_next(nxt, after=drawn)                          # the next step's rows are gathered beside this step's phase 2
         ahead.done_with(idx_stage)
         res_pin.copy_(eng.result, non_blocking=True)                   # D2H: loss / eigenvalues / penalty + gradient for the host optimiser
-        ahead.enqueue_next()                                           # the next step's draw, behind this step's kernels
+        ahead.enqueue_next()                                           # one more draw, behind this step's kernels
         torch.cuda.current_stream().synchronize()                      # update_step returns host values (:236)
         return float(out_pin[0])
 

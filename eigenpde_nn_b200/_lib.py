@@ -22,7 +22,7 @@ FLAG_GENERIC = 8        # never take the fused path (layer-wise generic family)
 ABI_VERSION = 4
 
 EXPORTS = ["epde_abi_version", "epde_error_string", "epde_param_count", "epde_num_sums", "epde_has_fused_path",
-           "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_step_sharded", "epde_forward",
+           "epde_workspace_bytes", "epde_step_partial", "epde_step_finish", "epde_step", "epde_step_sharded", "epde_gather_ahead", "epde_step_ahead", "epde_forward",
            "epde_minibatch_indices", "epde_minibatch_indices_device", "epde_minibatch_indices_device_split", "epde_mt_jump_poly",
            "epde_mt_jump_device",
            "epde_mt_seed", "epde_adam_step", "epde_average_accumulate",
@@ -67,6 +67,9 @@ def lib():
         L.epde_step.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp, vp]
         L.epde_step_sharded.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp,
                                         C.POINTER(EpdePeer), vp]
+        L.epde_gather_ahead.argtypes = [dp, vp, vp, vp, i64, vp, sz, C.c_int32, vp]
+        L.epde_step_ahead.argtypes = [dp, vp, vp, vp, i64, vp, vp, f64, f64, C.POINTER(f64), vp, sz, vp, vp, C.c_int32, C.c_int32,
+                                      C.c_int32, C.POINTER(EpdePeer), vp, vp]
         L.epde_forward.argtypes = [dp, vp, vp, i64, vp, vp, vp, sz, vp, vp]
         L.epde_minibatch_indices.argtypes = [vp, C.POINTER(C.c_int32), i64, i64, vp]
         L.epde_minibatch_indices_device.argtypes = [vp, i64, i64, i64, i64, vp, vp, vp]

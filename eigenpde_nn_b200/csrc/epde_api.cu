@@ -70,7 +70,9 @@ struct FusedWs {
   float* U; double* epart;    // per-row metric: u0 -> p of every net [k][tiles][d][256], k_metric's partial energy sums
   size_t total;
 };
-FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
+// slot: the tensor-core family keeps TWO sets of gathered rows (xt, wt) and maxima (mx), so that the gather of the next
+// step's minibatch (epde_gather_ahead, side stream) can fill one while the current step reads the other.
+FusedWs fused_ws(const epde_desc* D, int64_t B, void* base, int slot = 0) {
   char* p = (char*)base; size_t off = 0; FusedWs W;
   auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off = align_up(off + bytes, 256); return r; };
   W.pw = (float*)take((size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4);
@@ -86,6 +88,13 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base) {
   W.mx = (float*)take((size_t)(kMxWords + 1) * 4);
   W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
   W.stash = (float*)take(D->metric ? 0 : tc::stash_floats(B, D->k) * 4);      // (a metric runs the FFMA2 kernels: no stash)
+  {
+    const bool two = !D->metric && !(D->flags & EPDE_FLAG_FFMA2);
+    float* xt1 = (float*)take(two ? ntl * D->d_pad * GT * 4 : 0);
+    float* wt1 = (float*)take(two ? ntl * GT * 4 : 0);
+    float* mx1 = (float*)take(two ? (size_t)(kMxWords + 1) * 4 : 0);
+    if (slot == 1 && two) { W.xt = xt1; W.wt = wt1; W.mx = mx1; }
+  }
   W.U = (float*)take(D->metric ? (size_t)D->k * ntl * D->d * GT * 4 : 0);
   W.epart = (double*)take(D->metric ? (size_t)kMetricCtas * EPDE_MAX_K * 8 : 0);
   W.total = off;
@@ -154,25 +163,45 @@ cudaError_t launch_gather(const epde_desc* D, const float* X, const float* w, co
 }
 
 struct Deferred { int on, gx, g2; };      // epde_step: phase 1's final reduction is merged into the coefficient launch
+// Gather look-ahead (tensor-core family): slot = which set of gathered rows the step uses; pregathered = that set was filled
+// by epde_gather_ahead (the step skips its own gather); reserve = SMs the two persistent pass kernels leave free for the
+// gather of the NEXT step, which runs beside them on a second stream.
+struct Ahead { int slot, pregathered, reserve; };
+
+int gather_ahead(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B, void* ws, int slot,
+                 cudaStream_t st) {
+  FusedWs W = fused_ws(D, B, ws, slot);
+  cudaError_t e = cudaMemsetAsync(W.mx, 0, (size_t)(kMxWords + 1) * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)launch_gather(D, X, w, idx, B, W.xt, W.wt, st, 1, W.mx);
+}
 
 int fused_partial(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
-                  const float* params, const float* diag, void* ws, double* sums, cudaStream_t st, Deferred* df = nullptr) {
-  FusedWs W = fused_ws(D, B, ws);
+                  const float* params, const float* diag, void* ws, double* sums, cudaStream_t st, Deferred* df = nullptr,
+                  const Ahead* ah = nullptr) {
+  FusedWs W = fused_ws(D, B, ws, ah ? ah->slot : 0);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   const int impl = fused_impl(D);
+  const bool pre = impl == 1 && ah && ah->pregathered;
   cudaError_t e;
   if (impl != 1) k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
   else {
-    e = cudaMemsetAsync(W.mx, 0, (size_t)(kMxWords + 1) * 4, st);     // maxima are gathered with atomicMax; + k_fin2's ticket
-    if (e != cudaSuccess) return (int)e;
+    if (!pre) {
+      e = cudaMemsetAsync(W.mx, 0, (size_t)(kMxWords + 1) * 4, st);     // maxima are gathered with atomicMax; + k_fin2's ticket
+      if (e != cudaSuccess) return (int)e;
+    }
     rc = tc::pack(D->d, D->k, params, diag, W.pwt, W.nrm, st);
     if (rc) return rc;
   }
-  e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
-  if (e != cudaSuccess) return (int)e;
-  if (impl == 1)
-    return tc::partial(D->d, D->d_pad, D->k, nsm, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
+  if (!pre) {
+    e = launch_gather(D, X, w, idx, B, W.xt, W.wt, st, impl == 1, impl == 1 ? W.mx : nullptr);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (impl == 1) {
+    int nsm1 = nsm - (ah ? ah->reserve : 0); if (nsm1 < D->k) nsm1 = D->k;
+    return tc::partial(D->d, D->d_pad, D->k, nsm1, B, params, diag, W.xt, W.wt, W.pwt, W.ybuf, W.part, W.part2, sums,
                        W.mx, W.nrm, W.stash, st, df ? 1 : 0, df ? &df->gx : nullptr, df ? &df->g2 : nullptr);
+  }
   const int64_t npairs = (B + 1) / 2;
   int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
   if (grid > nsm) grid = nsm;
@@ -201,9 +230,9 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
 int fused_finish(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
                  const float* params, const float* diag, double beta, double alpha, const EigW& ew,
                  const double* sums, void* ws, double* out, float* grad, cudaStream_t st, const Deferred* df = nullptr,
-                 const Peer* peer = nullptr) {
+                 const Peer* peer = nullptr, const Ahead* ah = nullptr) {
   const Peer none = {nullptr, 0, 1, nullptr, 0};
-  FusedWs W = fused_ws(D, B, ws);
+  FusedWs W = fused_ws(D, B, ws, ah ? ah->slot : 0);
   int nsm; int rc = sm_count(&nsm); if (rc) return rc;
   const int impl = fused_impl(D);
   if (impl == 1 && df && df->on) {
@@ -215,7 +244,8 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
                               impl == 1 ? W.mx : nullptr, impl == 1 ? W.nrm : nullptr);
   if (impl == 1) {
     int gx = 0;
-    rc = tc::finish(D->d, D->d_pad, D->k, nsm, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
+    int nsm2 = nsm - (ah ? ah->reserve : 0); if (nsm2 < D->k) nsm2 = D->k;
+    rc = tc::finish(D->d, D->d_pad, D->k, nsm2, B, W.xt, W.wt, W.pwt, W.ybuf, W.coef, W.stash, W.pg, &gx, st);
     if (rc) return rc;
     cudaError_t e2 = launch_pdl(k_fin2<kFusedH>, dim3(D->k, fin2_items<kFusedH>(D->d)), dim3(1024), 0, st, (const float*)W.pg, gx,
                                 D->k, D->d, D->d_pad, params, diag, grad, peer ? *peer : none,
@@ -386,6 +416,50 @@ int epde_step_sharded(const epde_desc* D, const float* X, const float* w, const 
   Deferred df = {1, 0, 0};
   rc = fused_partial(D, X, w, idx, B, params, diag, ws, sums, (cudaStream_t)stream, &df); if (rc) return rc;
   return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, (cudaStream_t)stream, &df, &P);
+}
+
+int epde_gather_ahead(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B, void* ws,
+                      size_t ws_bytes, int32_t slot, void* stream) {
+  int rc = check_desc(D); if (rc) return rc;
+  if (!X || !w || !ws) return EPDE_ERR_NULL;
+  if (B < 1 || slot < 0 || slot > 1) return EPDE_ERR_ARG;
+  if (((uintptr_t)X & 15) || ((uintptr_t)ws & 255)) return EPDE_ERR_ALIGN;
+  if (!fused_ok(D) || fused_impl(D) != 1) return EPDE_ERR_UNSUPPORTED;
+  size_t need; rc = epde_workspace_bytes(D, B, &need); if (rc) return rc;
+  if (ws_bytes < need) return EPDE_ERR_WORKSPACE;
+  return gather_ahead(D, X, w, idx, B, ws, slot, (cudaStream_t)stream);
+}
+
+int epde_step_ahead(const epde_desc* D, const float* X, const float* w, const int64_t* idx, int64_t B,
+                    const float* params, const float* diag, double beta, double alpha, const double* h_eig_w,
+                    void* ws, size_t ws_bytes, double* out, float* grad, int32_t slot, int32_t pregathered,
+                    int32_t reserve_sms, const epde_peer* peer, void* event_phase1, void* stream) {
+  int rc = check_common(D, X, w, B, params, diag, ws, ws_bytes); if (rc) return rc;
+  if (!out || !h_eig_w || !grad) return EPDE_ERR_NULL;
+  if (slot < 0 || slot > 1 || reserve_sms < 0 || reserve_sms > 64) return EPDE_ERR_ARG;
+  if (!fused_ok(D) || fused_impl(D) != 1) return EPDE_ERR_UNSUPPORTED;      // tensor-core family only
+  Peer P = {nullptr, 0, 1, nullptr, 0};
+  if (peer) {
+    if (!peer->d_peer_bufs || !peer->d_epoch) return EPDE_ERR_NULL;
+    if (peer->world < 2 || peer->world > 32 || peer->rank < 0 || peer->rank >= peer->world || (peer->slot_bytes & 15) ||
+        param_count(D) * 4 > peer->slot_bytes || num_sums(D->k) * 8 > peer->slot_bytes)
+      return EPDE_ERR_ARG;
+    P = Peer{reinterpret_cast<char* const*>(peer->d_peer_bufs), peer->rank, peer->world, peer->d_epoch, (long long)peer->slot_bytes};
+  }
+  size_t need; epde_workspace_bytes(D, B, &need);
+  double* sums = (double*)((char*)ws + need - kSumsTail);
+  EigW ew; memset(&ew, 0, sizeof(ew));
+  for (int i = 0; i < D->k; i++) ew.v[i] = h_eig_w[i];
+  const Ahead ah = {slot, pregathered ? 1 : 0, reserve_sms};
+  Deferred df = {1, 0, 0};
+  const Ahead ah1 = {slot, pregathered ? 1 : 0, 0};      // phase 1 is bound by HBM itself: it keeps all SMs, and the caller
+  rc = fused_partial(D, X, w, idx, B, params, diag, ws, sums, (cudaStream_t)stream, &df, &ah1); if (rc) return rc;      // starts
+  if (event_phase1) {                                    // the gather only behind it (event_phase1)
+    cudaError_t e = cudaEventRecord((cudaEvent_t)event_phase1, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return fused_finish(D, X, w, idx, B, params, diag, beta, alpha, ew, sums, ws, out, grad, (cudaStream_t)stream, &df,
+                      peer ? &P : nullptr, &ah);
 }
 
 int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t B, const float* params,

@@ -19,7 +19,7 @@ size_t pack_floats(int d) { return (size_t)TcPack(d).total(); }
 size_t stash_floats(int64_t B, int k) { return (size_t)((B + 127) / 128) * (size_t)k * ST_TILE; }
 
 int pack(int d, int k, const float* params, const float* diag, float* pwt, float* nrm, cudaStream_t st) {
-  k_pack_tc<<<k, 256, 0, st>>>(params, diag, d, pwt, nrm);
+  k_pack_tc<<<dim3(k, 6), 256, 0, st>>>(params, diag, d, pwt, nrm);
   return (int)cudaGetLastError();
 }
 

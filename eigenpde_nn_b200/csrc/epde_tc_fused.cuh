@@ -233,14 +233,16 @@ __device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ 
   for (int e = threadIdx.x; e < H * d; e += blockDim.x) sW1[e] = W1[e];
   for (int e = threadIdx.x; e < d; e += blockDim.x) sdg[e] = diag_coeff[e];
   __syncthreads();
-  for (int e = threadIdx.x; e < TN * K1; e += blockDim.x) {
+  // gridDim.y CTAs share the elements of a net's image (one CTA per net took 12 us, all of it latency)
+  const int t0 = threadIdx.x + blockIdx.y * blockDim.x, ts = blockDim.x * gridDim.y;
+  for (int e = t0; e < TN * K1; e += ts) {
     const int n = e / K1, k = e % K1;
     float v = 0.f;
     if (n < H) v = (k < d) ? sW1[n * d + k] : (k == d ? b1[n] : 0.f);
     float hi, lo; split_tf32(v, hi, lo);
     o[L.W1f(0) + kmaj_off(n, k, K1)] = hi; o[L.W1f(1) + kmaj_off(n, k, K1)] = lo;
   }
-  for (int e = threadIdx.x; e < 5 * TN * TKH; e += blockDim.x) {
+  for (int e = t0; e < 5 * TN * TKH; e += ts) {
     const int m = e / (TN * TKH), r = e % (TN * TKH), n = r / TKH, k = r % TKH;
     float v = 0.f;
     if (n < H) {
@@ -257,6 +259,7 @@ __device__ __forceinline__ void pack_tc_body(int net, const float* __restrict__ 
     float hi, lo; split_tf32(v, hi, lo);
     o[L.mat(m, 0) + kmaj_off(n, k, TKH)] = hi; o[L.mat(m, 1) + kmaj_off(n, k, TKH)] = lo;
   }
+  if (blockIdx.y != 0) return;
   for (int e = threadIdx.x; e < TKH + 8; e += blockDim.x)
     o[L.w4() + e] = (e < H) ? W4[e] : (e == TKH ? b4[0] : 0.f);
   // induced infinity norms for the bounds of phase 2's fp16 staging (k_coef): max row / column abs sums, max |w4|

@@ -125,12 +125,101 @@ class StepEngine:
             device=self.device, dtype=torch.float32)
 
     # -- the step -----------------------------------------------------------------------------
-    def step_device(self, idx_dev, B, params_dev, alpha):
+    # -- gather look-ahead ---------------------------------------------------------------------
+    RESERVE_SMS = 10          # SMs the persistent pass kernels leave to the gather of the next step
+
+    def _ahead_ok(self):
+        if getattr(self, "_ahead_on", None) is None:
+            import os
+            self._ahead_on = bool(self.fused and self.metric is None and not (self._flags & (_lib.FLAG_FFMA2 | _lib.FLAG_GENERIC))
+                                  and (self.pg is None or self._fold_exchange())
+                                  and os.environ.get("EPDE_GATHER_AHEAD", "1") != "0")
+            if self._ahead_on:
+                lo, hi = torch.cuda.Stream.priority_range()          # (lowest, highest) = (0, -5)
+                self._hp = torch.cuda.Stream(device=self.device, priority=hi)       # the step's kernels
+                self._side = torch.cuda.Stream(device=self.device, priority=lo)     # the next step's gather
+                self._pending = None
+                self._await = None
+                self.RESERVE_SMS = int(os.environ.get("EPDE_RESERVE_SMS", self.RESERVE_SMS))
+                self._ev = [torch.cuda.Event() for _ in range(8)]
+                self._evi = 0
+        return self._ahead_on
+
+    def _event(self):
+        self._evi = (self._evi + 1) % len(self._ev)
+        return self._ev[self._evi]
+
+    def compute_stream(self):
+        """The (high-priority) stream the look-ahead steps run on; a caller that makes it the current stream
+        (`with torch.cuda.stream(engine.compute_stream()): ...`) saves the two hand-over events per step.  None when the
+        gather look-ahead does not apply to this engine."""
+        return self._hp if self._ahead_ok() else None
+
+    def _step_ahead(self, idx_dev, B, params_dev, alpha, next_idx):
+        """The step with the gather of the NEXT step's rows running beside it (`epde_gather_ahead` on a low-priority stream,
+        the step itself on a high-priority one with `RESERVE_SMS` SMs left free by its two persistent kernels).  The rows of
+        THIS step were gathered during the previous call if it was given this index tensor as `next_idx`."""
+        ws = self._workspace(B)
+        cur = torch.cuda.current_stream(self.device)
+        hp, side = self._hp, self._side
+        pend, self._pending = self._pending, None
+        pre = int(pend is not None and pend[0] == idx_dev.data_ptr() and pend[1] == B and pend[4] == self.ws_generation)
+        slot = pend[2] if pend is not None else 0
+        if pend is not None and not pre:
+            slot = 1 - pend[2]              # an unused look-ahead may still be writing its set: take the other one
+        same = cur == hp                     # the caller already works on the engine's compute stream: no hand-over events
+        if not same:
+            e0 = self._event(); e0.record(cur)   # everything the caller has enqueued so far (parameters, previous results read)
+            hp.wait_event(e0)
+        if pre:
+            hp.wait_event(pend[3])
+        args = (C.byref(self.desc), _ptr(self.X), _ptr(self.w), _ptr(idx_dev), C.c_int64(B), _ptr(params_dev), _ptr(self.diag))
+        peer = C.byref(self._peer) if (self.pg is not None and self._fold_exchange()) else None
+        ep = self._event() if next_idx is not None else None
+        if ep is not None:
+            ep.record(hp)                   # (creates the CUDA event; the library records it again between the two phases)
+        _lib.check(self.lib.epde_step_ahead(*args, C.c_double(self.beta), C.c_double(alpha), self._eigw_c, _ptr(ws),
+                                            C.c_size_t(ws.numel()), _ptr(self.out), _ptr(self.grad), slot, pre,
+                                            self.RESERVE_SMS if next_idx is not None else 0, peer,
+                                            C.c_void_p(ep.cuda_event) if ep is not None else None, C.c_void_p(hp.cuda_stream)),
+                   "epde_step_ahead")
+        if not same:
+            e1 = self._event(); e1.record(hp)
+            cur.wait_event(e1)
+        if next_idx is not None:
+            self._await = (ep, 1 - slot, B)
+            if next_idx is not LATER:
+                self.gather_next(next_idx)
+        return self.out, self.grad
+
+    def gather_next(self, next_idx, after=None):
+        """Enqueue the look-ahead gather announced by `step_device(..., next_idx=LATER)`: the rows of `next_idx` (device
+        int64, same B) for the next call.  `after`: an event the indices become valid with (e.g. a draw on another stream)."""
+        ep, slot, B = self._await
+        self._await = None
+        ws = self._workspace(B)
+        side = self._side
+        # the set was last read by the step BEFORE the one just enqueued, which is complete.  The gather starts behind phase 1
+        # of the step just enqueued (bound by HBM itself) and runs beside its phase 2 on the SMs that kernel leaves free.
+        side.wait_event(ep)
+        if after is not None:
+            side.wait_event(after)
+        _lib.check(self.lib.epde_gather_ahead(C.byref(self.desc), _ptr(self.X), _ptr(self.w), _ptr(next_idx), C.c_int64(B),
+                                              _ptr(ws), C.c_size_t(ws.numel()), slot, C.c_void_p(side.cuda_stream)),
+                   "epde_gather_ahead")
+        eg = self._event(); eg.record(side)
+        self._pending = (next_idx.data_ptr(), B, slot, eg, self.ws_generation)
+
+    def step_device(self, idx_dev, B, params_dev, alpha, next_idx=None):
         """Asynchronous step on the current stream.  idx_dev: int64 device tensor or None.
 
         Returns (out_scalars fp64 device tensor, grad fp32 device tensor), both owned by the engine.
         With a process group the batch is the union of all ranks' idx slices.
+        next_idx: the index tensor of the NEXT call (same B), if the caller already has it - the minibatch does not depend
+        on this step's result (src/data_set.py:67) -: its rows are gathered while this step computes (`_step_ahead`).
         """
+        if idx_dev is not None and (next_idx is not None or getattr(self, "_pending", None) is not None) and self._ahead_ok():
+            return self._step_ahead(idx_dev, B, params_dev, alpha, next_idx)
         ws = self._workspace(B)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         args = (C.byref(self.desc), _ptr(self.X), _ptr(self.w), _ptr(idx_dev), C.c_int64(B), _ptr(params_dev),
@@ -323,9 +412,11 @@ class DeviceMinibatch:
         self.state.copy_(J["states"][parts])        # same address every step: the draw can sit inside a replayed CUDA graph
         return out
 
-    def draw(self, B_total, out=None, lo=0, n=None):
+    def draw(self, B_total, out=None, lo=0, n=None, split=False):
         """Enqueue B_total draws on the current stream; the indices of draws [lo, lo + n) go to `out` (int64, device).
-        A proper slice (a rank of a sharded step) is reached by jump-ahead: only its own 2 * n words are generated."""
+        A proper slice (a rank of a sharded step) is reached by jump-ahead: only its own 2 * n words are generated.
+        split: use the jump-ahead path for a whole-stream draw too (several CTAs generate at once; the generator is then left
+        as the 624-word window at the new position instead of CPython's (block, position) pair - the same stream)."""
         assert self.seeded, "call seed_from_python() first"
         n = B_total - lo if n is None else n
         if out is None:
@@ -333,7 +424,7 @@ class DeviceMinibatch:
         if B_total == 0:
             return out
         import os
-        if (lo != 0 or n != B_total) and os.environ.get("EPDE_MT_JUMP", "1") != "0":      # (a whole-stream draw stays sequential:
+        if (lo != 0 or n != B_total or split) and os.environ.get("EPDE_MT_JUMP", "1") != "0":      # (a whole-stream draw stays sequential:
             # it leaves the generator exactly as CPython would show it, block and position)
             return self._draw_slice(B_total, out, lo, n)
         if self._raw is None or self._raw.numel() < 2 * B_total:
@@ -345,52 +436,68 @@ class DeviceMinibatch:
         return out
 
 
+LATER = object()        # step_device(..., next_idx=LATER): the next minibatch is announced afterwards with gather_next()
+
+
 class DrawAhead:
     """Draws the next step's minibatch on a second stream while the current step computes (the index stream does not
     depend on the step's result; the generator is a single CTA and the step's kernels leave an SM idle).
         ahead = DrawAhead(mb, B_total, lo, n); ahead.start()
         for ...: idx = ahead.take(); <enqueue the step reading idx>; ahead.done_with(idx) ..."""
 
-    def __init__(self, mb: DeviceMinibatch, B_total, lo=0, n=None):
-        self.mb, self.B_total, self.lo = mb, B_total, lo
+    def __init__(self, mb: DeviceMinibatch, B_total, lo=0, n=None, split=False, depth=1):
+        """depth: draws kept in flight (1: the next step's; 2: also the one after it, so that the next step's indices are
+        complete while the current step runs - what the gather look-ahead of StepEngine needs)."""
+        self.mb, self.B_total, self.lo, self.split, self.depth = mb, B_total, lo, split, depth
         self.n = B_total - lo if n is None else n
         dev = mb.device
-        self.buf = [torch.empty(self.n, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.nb = depth + 1
+        self.buf = [torch.empty(self.n, dtype=torch.int64, device=dev) for _ in range(self.nb)]
         self.stream = torch.cuda.Stream(device=dev)
-        self.ready = [torch.cuda.Event() for _ in range(2)]
-        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(self.nb)]
+        self.free = [torch.cuda.Event() for _ in range(self.nb)]
         for e in self.free:
             e.record(torch.cuda.current_stream(dev))
         self.stream.wait_stream(torch.cuda.current_stream(dev))      # the uploaded state is visible to the side stream
         self.head = self.tail = 0
 
     def start(self):
-        self._enqueue()
+        for _ in range(self.depth):
+            self._enqueue()
         return self
 
     def _enqueue(self):
-        b = self.head & 1
+        b = self.head % self.nb
         self.stream.wait_event(self.free[b])
         with torch.cuda.stream(self.stream):
-            self.mb.draw(self.B_total, self.buf[b], self.lo, self.n)
+            self.mb.draw(self.B_total, self.buf[b], self.lo, self.n, split=self.split)
             self.ready[b].record(self.stream)
         self.head += 1
+        return self.buf[b], self.ready[b]
 
     def take(self, defer=False):
         """Indices of the current step; the draw of the following step starts right away on the side stream - or, with
         defer=True, when the caller says so (`enqueue_next()`, after it has launched the step: enqueueing the draw costs
         host time that would otherwise sit between the previous step's results and this step's first kernel)."""
-        b = self.tail & 1
+        b = self.tail % self.nb
         torch.cuda.current_stream(self.mb.device).wait_event(self.ready[b])
         if not defer:
             self._enqueue()
         return self.buf[b]
 
+    def peek(self, ahead=1):
+        """(index buffer, drawn-event) of the step `ahead` steps after the one take() returns next; it must be in flight
+        already (ahead < depth before the current step's enqueue_next)."""
+        assert self.tail + ahead < self.head
+        b = (self.tail + ahead) % self.nb
+        return self.buf[b], self.ready[b]
+
     def enqueue_next(self):
-        self._enqueue()
+        """Returns (index buffer of the newly enqueued draw, event that marks it drawn)."""
+        return self._enqueue()
 
     def done_with(self, idx):
-        self.free[self.tail & 1].record(torch.cuda.current_stream(self.mb.device))
+        self.free[self.tail % self.nb].record(torch.cuda.current_stream(self.mb.device))
         self.tail += 1
 
     def finish(self):

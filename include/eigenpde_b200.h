@@ -36,7 +36,8 @@ extern "C" {
 #endif
 
 #define EPDE_ABI_VERSION 4      /* 2: epde_desc.metric, epde_md_align; 3: EPDE_FLAG_FFMA2 replaces epde_set_fused_impl,
-                                   device-side minibatch generator; 4: epde_step_sharded, EPDE_FLAG_GENERIC */
+                                   device-side minibatch generator; 4: epde_step_sharded, EPDE_FLAG_GENERIC,
+                                   epde_gather_ahead / epde_step_ahead, epde_minibatch_indices_device_split */
 #define EPDE_MAX_LAYERS 8   /* Linear layers per net */
 #define EPDE_MAX_K 8        /* eigenfunctions (nets) */
 
@@ -269,6 +270,24 @@ int epde_step_sharded(const epde_desc* desc, const float* d_X, const float* d_w,
                       const float* d_params, const float* d_diag, double beta, double alpha, const double* h_eig_w,
                       void* d_ws, size_t ws_bytes, double* d_out_scalars, float* d_grad, const epde_peer* peer,
                       void* stream);
+
+/*
+ * Gather look-ahead (tensor-core family; EPDE_ERR_UNSUPPORTED otherwise).  The minibatch of step i + 1 does not depend on
+ * the result of step i (src/data_set.py:67), and the gather of its rows X[idx[n]][:] is the one HBM-bound kernel of the
+ * step, while the two long kernels of step i are not.  epde_gather_ahead, called on a SECOND (lower-priority) stream while
+ * step i runs, fills set `slot` (0 / 1) of the workspace's gathered-row buffers; epde_step_ahead is epde_step (peer == NULL)
+ * or epde_step_sharded on set `slot`, skipping its own gather if `pregathered`, and keeping `reserve_sms` SMs free of its
+ * persistent phase-2 kernel so that the concurrent gather for step i + 1 has somewhere to run.  Phase 1 is bound by HBM
+ * itself (it writes the stash), so the gather should start behind it: event_phase1 (a cudaEvent_t, or NULL) is recorded on
+ * `stream` between the phases for the gather's stream to wait on.  The caller orders the two streams with events (set
+ * `slot` is read by step i until its last kernel, and written by the gather for step i + 2) and alternates the slots.
+ */
+int epde_gather_ahead(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx, int64_t B,
+                      void* d_ws, size_t ws_bytes, int32_t slot, void* stream);
+int epde_step_ahead(const epde_desc* desc, const float* d_X, const float* d_w, const int64_t* d_idx, int64_t B,
+                    const float* d_params, const float* d_diag, double beta, double alpha, const double* h_eig_w,
+                    void* d_ws, size_t ws_bytes, double* d_out_scalars, float* d_grad, int32_t slot, int32_t pregathered,
+                    int32_t reserve_sms, const epde_peer* peer, void* event_phase1, void* stream);
 
 int epde_peer_allreduce(void* const* d_peer_bufs, int rank, int world, uint32_t epoch, const void* src, void* dst,
                         int64_t n, int is_f64, int64_t slot_bytes, void* stream);

@@ -592,3 +592,33 @@ def test_minibatch_pipeline_delivers_every_batch():
             pipe.prefetch(pins[i + 1])
         torch.cuda.synchronize()
         assert torch.equal(chk.cpu(), pins[i])
+
+
+def test_gather_look_ahead_equals_plain_steps():
+    """`step_device(..., next_idx=...)`: the rows of the next minibatch are gathered on a second stream while the step
+    computes (epde_gather_ahead / epde_step_ahead, two sets of gathered rows, SMs reserved for the gather).  A chain of steps
+    with fresh indices must give what the plain steps give (the reserve changes the CTA partition of the sums: round-off
+    level differences only), also when the announced minibatch is not the one that comes."""
+    c = _rand_case(4242, 50, 3, [20, 20, 20], 60000, 30011)
+    rng = np.random.default_rng(7)
+    idxs = [torch.from_numpy(rng.integers(0, 60000, 30011)).cuda() for _ in range(6)]
+    flat = _flat(c["params"])
+    plain = _engine(c)
+    ahead = _engine(c)
+    assert ahead._ahead_ok()
+    want = []
+    for ix in idxs:
+        o, g = plain.step_device(ix, ix.numel(), flat, c["alpha"])
+        want.append((o.clone(), g.clone()))
+    seq = [0, 1, 2, 3, 4, 5]
+    for i, j in enumerate(seq):
+        nxt = idxs[seq[i + 1]] if i + 1 < len(seq) else None
+        if i == 2:
+            nxt = idxs[0]                      # announce a minibatch that does not come: the step must gather for itself
+        o, g = ahead.step_device(idxs[j], idxs[j].numel(), flat, c["alpha"], next_idx=nxt)
+        wo, wg = want[j]
+        assert float(((o[:4] - wo[:4]).abs() / wo[:4].abs()).max()) < 1e-9, (i, o[:4], wo[:4])
+        assert float((g - wg).norm() / wg.norm()) < 2e-6, i
+    c["idx"] = idxs[5].cpu().numpy()
+    res = ahead.step(c["idx"], flat, c["alpha"])             # host-facing call after a look-ahead chain
+    _check(c, _oracle(c), res)
