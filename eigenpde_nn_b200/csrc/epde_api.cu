@@ -89,7 +89,7 @@ FusedWs fused_ws(const epde_desc* D, int64_t B, void* base, int slot = 0) {
   W.nrm = (float*)take((size_t)kNrmPerNet * EPDE_MAX_K * 4);
   W.stash = (float*)take(D->metric ? 0 : tc::stash_floats(B, D->k) * 4);      // (a metric runs the FFMA2 kernels: no stash)
   {
-    const bool two = !D->metric && !(D->flags & EPDE_FLAG_FFMA2);
+    const bool two = !D->metric;      // (both kernel families: the workspace layout does not depend on EPDE_FLAG_FFMA2)
     float* xt1 = (float*)take(two ? ntl * D->d_pad * GT * 4 : 0);
     float* wt1 = (float*)take(two ? ntl * GT * 4 : 0);
     float* mx1 = (float*)take(two ? (size_t)(kMxWords + 1) * 4 : 0);
