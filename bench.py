@@ -373,6 +373,16 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     out_h = eng.out.cpu().numpy()
+    # self-check of the look-ahead path: the last timed step (rows gathered one step ahead, SMs reserved) against the same step
+    # with its own gather (the pending look-ahead does not match it, so the step gathers for itself)
+    ahead_check = None
+    if eng.compute_stream() is not None:
+        last = idx_dev[(args.steps - 1) % nbatch]
+        o_a, g_a = eng.out.clone(), eng.grad.clone()
+        eng.step_device(last, B, params, ALPHA)
+        rel_o = float(((eng.out[:4] - o_a[:4]).abs() / o_a[:4].abs().clamp_min(1e-300)).max())
+        rel_g = float((eng.grad - g_a).norm() / g_a.norm())
+        ahead_check = {"scalars_max_rel": rel_o, "grad_norm_rel": rel_g, "ok": bool(rel_o <= 1e-9 and rel_g <= 1e-5)}
 
     # ---- per-phase timing of the dominant kernel (k_pass2 inside epde_step_finish) ----------
     import ctypes as C
@@ -494,6 +504,10 @@ def main():
     }
     if parity is not None:
         line["parity"] = parity
+    if ahead_check is not None:
+        line["gather_look_ahead"] = dict(ahead_check, reserve_sms=eng.RESERVE_SMS,
+                                         note="value and e2e announce the next (already drawn) minibatch to every step: its rows are "
+                                              "gathered on a second stream beside phase 2; EPDE_GATHER_AHEAD=0 disables it")
     if world == 1 and not args.no_extra and KNETS == 3:
         line["extra"] = extra_workloads(dev, X, w)
     if world == 1 and not args.no_cpu_baseline:

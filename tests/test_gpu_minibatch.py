@@ -161,3 +161,25 @@ def test_draw_ahead_pipeline_matches_sequential_draws():
         ahead.done_with(idx)
         assert torch.equal(got.cpu(), torch.from_numpy(want[i])), i
     ahead.finish()
+
+
+def test_draw_ahead_with_two_draws_in_flight():
+    """DrawAhead(depth=2): the next step's indices are complete (peek) while the current step runs and one more draw is
+    being generated - the same stream as sequential draws, in order."""
+    from eigenpde_nn_b200.engine import DrawAhead
+    K, B, steps = 1_000_003, 70_001, 7
+    random.seed(31337)
+    saved = random.getstate()
+    want = [_host_draw(K, B) for _ in range(steps + 2)]
+    random.setstate(saved)
+    mb = _mb(K).seed_from_python()
+    ahead = DrawAhead(mb, B, depth=2).start()
+    for i in range(steps):
+        idx = ahead.take(defer=True)
+        nxt, drawn = ahead.peek(1)
+        drawn.synchronize()
+        assert np.array_equal(nxt.cpu().numpy(), want[i + 1])
+        assert np.array_equal(idx.cpu().numpy(), want[i])
+        ahead.done_with(idx)
+        ahead.enqueue_next()
+    ahead.finish()
