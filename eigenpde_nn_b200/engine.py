@@ -100,6 +100,9 @@ class StepEngine:
     # -- buffers ------------------------------------------------------------------------------
     def _workspace(self, B):
         if self._ws is None or B > self._ws_B:
+            if getattr(self, "_pending", None) is not None or getattr(self, "_await", None) is not None:
+                self._side.synchronize()        # a look-ahead gather may still be writing into the workspace that goes away
+                self._pending = self._await = None
             need = C.c_size_t()
             _lib.check(self.lib.epde_workspace_bytes(C.byref(self.desc), B, C.byref(need)), "epde_workspace_bytes")
             self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=self.device)
