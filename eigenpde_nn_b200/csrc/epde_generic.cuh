@@ -342,6 +342,13 @@ inline GenericPlan generic_plan(const epde_desc* D, int64_t B, void* base) {
   const size_t per_sample = (size_t)4 * (5 * (P.sumh + 1) + 3 * P.maxn + 2 * D->d_pad + 4);
   int64_t bc = (int64_t)((size_t)(1536u << 20) / per_sample);      // <= 1.5 GB of per-chunk matrices
   bc = bc / 256 * 256; if (bc < 256) bc = 256; if (bc > 65536) bc = 65536;
+  {
+    // whole waves of the tcgen05 GEMM: 128-row tiles, ceil(maxn / 128) column tiles, two CTAs per SM on 148 SMs - a chunk of
+    // 65 536 rows of a 256-wide layer is 3.46 waves (the last one 46 % full), 56 832 rows are exactly three
+    const int64_t ntile = (P.maxn + 127) / 128;
+    const int64_t wave_rows = 128 * ((2 * 148) / ntile);
+    if (wave_rows >= 256 && bc > wave_rows && B > wave_rows) bc = bc / wave_rows * wave_rows;
+  }
   if (bc > B) bc = B;
   P.Bc = bc;
   char* p = (char*)base; size_t off = 0;
