@@ -1,8 +1,7 @@
 import os, sys, random, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from eigenpde_nn_b200.engine import DeviceMinibatch
-from oracle import minibatch as om
 K = 5_000_000
 for (Btot, world) in [(1 << 21, 8), (1 << 23, 8), (3 * 300007, 3)]:
     random.seed(99)
