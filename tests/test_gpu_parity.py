@@ -594,14 +594,15 @@ def test_minibatch_pipeline_delivers_every_batch():
         assert torch.equal(chk.cpu(), pins[i])
 
 
-def test_gather_look_ahead_equals_plain_steps():
+@pytest.mark.parametrize("d,k,B", [(50, 3, 30011), (2, 2, 777), (30, 6, 4099), (60, 1, 129)])
+def test_gather_look_ahead_equals_plain_steps(d, k, B):
     """`step_device(..., next_idx=...)`: the rows of the next minibatch are gathered on a second stream while the step
     computes (epde_gather_ahead / epde_step_ahead, two sets of gathered rows, SMs reserved for the gather).  A chain of steps
     with fresh indices must give what the plain steps give (the reserve changes the CTA partition of the sums: round-off
     level differences only), also when the announced minibatch is not the one that comes."""
-    c = _rand_case(4242, 50, 3, [20, 20, 20], 60000, 30011)
+    c = _rand_case(4242 + d, d, k, [20, 20, 20], 60000, B)
     rng = np.random.default_rng(7)
-    idxs = [torch.from_numpy(rng.integers(0, 60000, 30011)).cuda() for _ in range(6)]
+    idxs = [torch.from_numpy(rng.integers(0, 60000, B)).cuda() for _ in range(6)]
     flat = _flat(c["params"])
     plain = _engine(c)
     ahead = _engine(c)
