@@ -53,8 +53,20 @@ def main():
         dist.all_gather(gathered, same)
         identical = all(torch.equal(gathered[0], t) for t in gathered)      # every rank holds bit-identical results
         used = ("peer-folded" if eng._fold_exchange() else "peer") if eng._exchange is not None else "nccl"
+        ahead_rel = None
+        if eng._ahead_ok():
+            # the gather look-ahead on every rank: a chain of steps that announce the next slice; the last one must give
+            # what the plain sharded step gave on the same slice
+            g_plain, o_plain = grad.clone(), out.clone()      # (the engine owns `grad` / `out`: the chain overwrites them)
+            rng2 = np.random.default_rng(1000 + rank)
+            others = [torch.from_numpy(rng2.integers(0, c["X"].shape[0], hi - lo)).to(dev) for _ in range(2)]
+            chain = others + [idx_dev]
+            for i, ix in enumerate(chain):
+                oa, ga = eng.step_device(ix, hi - lo, flat, c["alpha"], next_idx=chain[i + 1] if i + 1 < len(chain) else None)
+            ahead_rel = float((ga - g_plain).norm() / g_plain.norm())
+            assert ahead_rel <= 2e-6 and float((oa[0] - o_plain[0]).abs() / o_plain[0].abs()) <= 1e-9, (ahead_rel, oa[0], o_plain[0])
         verdict["cases"].append(dict(d=d, k=k, B=B, requested=force, exchange=used, worst_vs_oracle=float(worst),
-                                     grad_vs_single_rank=rel, identical_on_all_ranks=bool(identical)))
+                                     grad_vs_single_rank=rel, identical_on_all_ranks=bool(identical), look_ahead_vs_plain=ahead_rel))
         assert rel <= 1e-5 and identical, verdict["cases"][-1]
         del eng, single
     if rank == 0:
