@@ -24,7 +24,11 @@ constexpr int kFusedH = 20;
 // kernel family of the fused path: EPDE_FLAG_FFMA2 in the descriptor selects the FFMA2 kernels (epde_fused.cuh), the
 // default are the tcgen05 kernels (epde_tc_fused.cuh).  The choice travels with the descriptor: no process-wide state.
 // A per-row metric (MD alignment layer) is implemented by the FFMA2 kernels only.
-inline int fused_impl(const epde_desc* D) { return ((D->flags & EPDE_FLAG_FFMA2) || D->metric) ? 0 : 1; }
+// ... and so are the activations other than Tanh (Act<true> in epde_fused.cuh).
+inline int fused_impl(const epde_desc* D) {
+  return ((D->flags & EPDE_FLAG_FFMA2) || D->metric || D->act_id != EPDE_ACT_TANH) ? 0 : 1;
+}
+inline bool general_act(const epde_desc* D) { return D->act_id != EPDE_ACT_TANH; }
 constexpr size_t kSumsTail = 2048;
 constexpr int64_t kFwdSlab = 1 << 18;   // samples per slab of epde_forward (bounds its workspace)
 
@@ -46,7 +50,13 @@ int check_desc(const epde_desc* D) {
 bool fused_ok(const epde_desc* D) {
   if (D->metric && (D->d > 2 * kFusedH || (D->flags & EPDE_FLAG_GENERIC))) return false;   // per-row metric: u0 / p live in 2 H shared-memory rows
   if (D->flags & EPDE_FLAG_GENERIC) return false;
-  if (D->n_layers != 4 || D->act_id != EPDE_ACT_TANH) return false;
+  if (D->n_layers != 4) return false;
+  if (D->act_id != EPDE_ACT_TANH) {      // the FFMA2 kernels take every activation whose derivatives are functions of its value
+    // (not Tanhshrink: its derivatives are not functions of its value; not Sigmoid: all-positive units make the gradient a
+    //  small difference of large sums, and the layer-wise family - fp64 accumulation of every weight gradient - is the
+    //  one that holds the reference's golden Sigmoid case to 2e-4)
+    if (D->act_id == EPDE_ACT_TANHSHRINK || D->act_id == EPDE_ACT_SIGMOID || D->metric) return false;
+  }
   if (D->widths[1] != kFusedH || D->widths[2] != kFusedH || D->widths[3] != kFusedH) return false;
   if (D->k > 6) return false;
   if (D->d + 1 > 8 * 8) return false;           // tensor-core family: layer-1 k-steps 8 ks1 >= d + 1 with ks1 <= 8 (x staging rows TXR = 64)
@@ -130,7 +140,13 @@ k_reduce_part(const double* __restrict__ part, int nb, int ns, double* __restric
 
 template <int K>
 cudaError_t launch_pass1(int grid, size_t smem, cudaStream_t st, const float* xt, const float* wt, int64_t B, int d,
-                         int d_pad, const float* pw, float* ybuf, double* part, float* U) {
+                         int d_pad, const float* pw, float* ybuf, double* part, float* U, int act_id) {
+  if (act_id != EPDE_ACT_TANH) {       // general activation (never together with a per-row metric: fused_ok)
+    cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_pass1<kFusedH, K, false, true><<<grid, P1_THREADS, smem, st>>>(xt, wt, B, d, d_pad, pw, ybuf, part, nullptr, act_id);
+    return cudaGetLastError();
+  }
   if (U) {
     cudaError_t e = cudaFuncSetAttribute(k_pass1<kFusedH, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -208,12 +224,12 @@ int fused_partial(const epde_desc* D, const float* X, const float* w, const int6
   const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
   float* U = D->metric ? W.U : nullptr;
   switch (D->k) {
-    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
-    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
-    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
-    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
-    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
-    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U); break;
+    case 1: e = launch_pass1<1>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
+    case 2: e = launch_pass1<2>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
+    case 3: e = launch_pass1<3>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
+    case 4: e = launch_pass1<4>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
+    case 5: e = launch_pass1<5>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
+    default: e = launch_pass1<6>(grid, smem, st, W.xt, W.wt, B, D->d, D->d_pad, W.pw, W.ybuf, W.part, U, D->act_id); break;
   }
   if (e != cudaSuccess) return (int)e;
   int ne = 0;
@@ -257,7 +273,12 @@ int fused_finish(const epde_desc* D, const float* X, const float* w, const int64
   if (gx > ntiles) gx = (int)ntiles;
   const size_t smem = pass2_smem_bytes<kFusedH>(D->d, D->d_pad);
   cudaError_t e;
-  if (D->metric) {
+  if (general_act(D)) {
+    e = cudaFuncSetAttribute(k_pass2<kFusedH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_pass2<kFusedH, false, true><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
+                                                                             W.coef, W.pg, nullptr, D->act_id);
+  } else if (D->metric) {
     e = cudaFuncSetAttribute(k_pass2<kFusedH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     k_pass2<kFusedH, true><<<dim3(gx, D->k), P2_THREADS, smem, st>>>(W.xt, W.wt, B, D->d, D->d_pad, D->k, W.pw, W.ybuf,
@@ -478,7 +499,9 @@ int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t
   int nsm; rc = sm_count(&nsm); if (rc) return rc;
   k_pack<kFusedH><<<D->k, 256, 0, st>>>(params, diag, D->d, D->d_pad, W.pw);
   const size_t smem = (size_t)D->k * PackLayout<kFusedH>(D->d_pad).total() * 4;
-  cudaError_t e = cudaFuncSetAttribute(k_forward<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = general_act(D)
+      ? cudaFuncSetAttribute(k_forward<kFusedH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+      : cudaFuncSetAttribute(k_forward<kFusedH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   for (int64_t b0 = 0; b0 < B; b0 += kFwdSlab) {
     const int64_t bc = (B - b0 < kFwdSlab) ? B - b0 : kFwdSlab;
@@ -488,7 +511,10 @@ int epde_forward(const epde_desc* D, const float* X, const int64_t* idx, int64_t
     const int64_t npairs = (bc + 1) / 2;
     int grid = (int)((npairs + P1_THREADS - 1) / P1_THREADS);
     if (grid > 4 * nsm) grid = 4 * nsm;
-    k_forward<kFusedH><<<grid, P1_THREADS, smem, st>>>(W.xt, bc, D->d, D->d_pad, D->k, W.pw, y + b0 * D->k);
+    if (general_act(D))
+      k_forward<kFusedH, true><<<grid, P1_THREADS, smem, st>>>(W.xt, bc, D->d, D->d_pad, D->k, W.pw, y + b0 * D->k, D->act_id);
+    else
+      k_forward<kFusedH><<<grid, P1_THREADS, smem, st>>>(W.xt, bc, D->d, D->d_pad, D->k, W.pw, y + b0 * D->k);
   }
   return (int)cudaGetLastError();
 }

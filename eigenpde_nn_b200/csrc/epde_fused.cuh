@@ -194,11 +194,63 @@ k_gather128(const float* __restrict__ X, const float* __restrict__ w, const int6
   gather128_body<DUMMY>(X, w, idx, B, d_pad, xt, wt, mx, (int64_t)blockIdx.x);
 }
 
+// ---- activation (phi, phi', phi'' as a parameter of the fused kernels) --------------------------------
+// The kernels keep only a = phi(z) of every hidden unit, so the derivatives are written as functions of a:
+//   d1(a) = phi'(z),   r(a) = phi''(z) / phi'(z)   (phi'' u = r(a) * g with g = phi' u: what the reverse sweeps use)
+// GA = false: Tanh, the expressions the kernels were written with (d1 = 1 - a^2, r = -2 a).  GA = true: the activation is a
+// run-time id (CTA-uniform branch) among those invertible this way - Sigmoid, Softplus, LogSigmoid, ELU / CELU, ReLU
+// (torch.nn defaults, src/network_arch.py:27-34); Tanhshrink is not (z - tanh z does not determine tanh z cheaply) and stays
+// on the layer-wise family.
+template <bool GA>
+struct Act {
+  int id;
+  __device__ __forceinline__ float f1(float z) const {
+    switch (id) {
+      case EPDE_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+      case EPDE_ACT_SOFTPLUS: return z > 20.f ? z : (z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z)));
+      case EPDE_ACT_LOGSIGMOID: return z < 0.f ? z - log1pf(expf(z)) : -log1pf(expf(-z));
+      case EPDE_ACT_ELU: return z > 0.f ? z : expm1f(z);
+      default: return z > 0.f ? z : 0.f;                               // ReLU
+    }
+  }
+  __device__ __forceinline__ float d1s(float a) const {
+    switch (id) {
+      case EPDE_ACT_SIGMOID: return a * (1.f - a);
+      case EPDE_ACT_SOFTPLUS: return -expm1f(-a);                      // sigmoid(z) = 1 - exp(-softplus(z))
+      case EPDE_ACT_LOGSIGMOID: return -expm1f(a);                     // 1 - sigmoid(z) = 1 - exp(logsigmoid(z))
+      case EPDE_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+      default: return a > 0.f ? 1.f : 0.f;
+    }
+  }
+  __device__ __forceinline__ float rs(float a) const {
+    switch (id) {
+      case EPDE_ACT_SIGMOID: return 1.f - 2.f * a;
+      case EPDE_ACT_SOFTPLUS: return expf(-a);                         // 1 - sigmoid(z)
+      case EPDE_ACT_LOGSIGMOID: return -expf(a);                       // -sigmoid(z)
+      case EPDE_ACT_ELU: return a > 0.f ? 0.f : 1.f;
+      default: return 0.f;
+    }
+  }
+  __device__ __forceinline__ float2 f(float2 z) const {
+    if (!GA) return tanh2(z);
+    return make_float2(f1(z.x), f1(z.y));
+  }
+  __device__ __forceinline__ float2 d1(float2 a) const {
+    if (!GA) return ffma2(make_float2(-a.x, -a.y), a, splat(1.0f));
+    return make_float2(d1s(a.x), d1s(a.y));
+  }
+  __device__ __forceinline__ float2 r(float2 a) const {
+    if (!GA) return make_float2(-2.f * a.x, -2.f * a.y);
+    return make_float2(rs(a.x), rs(a.y));
+  }
+};
+
 // layer 1: a1 = tanh(W1 x + b1); x_j of the sample pair is one coalesced float2 of the transposed
 // tile, software-pipelined PF columns ahead of the FFMA2 stream.
-template <int H, int PF = 8>
+template <int H, int PF = 8, bool GA = false>
 __device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1T, const float* __restrict__ sb1,
-                                           const float* __restrict__ xcol, int d, int d_pad, float2 (&a1)[H]) {
+                                           const float* __restrict__ xcol, int d, int d_pad, float2 (&a1)[H],
+                                           const Act<GA> act = Act<GA>{0}) {
   bias2<H>(sb1, a1);
   float2 cur[PF];
 #pragma unroll
@@ -228,17 +280,17 @@ __device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1T, const
     for (int q = 0; q < PF; q++) cur[q] = nxt[q];
   }
 #pragma unroll
-  for (int o = 0; o < H; o++) a1[o] = tanh2(a1[o]);
+  for (int o = 0; o < H; o++) a1[o] = act.f(a1[o]);
 }
 
 // hidden layer: a_out = tanh(W a_in + b), weights in [in][out] layout
-template <int H>
+template <int H, bool GA = false>
 __device__ __forceinline__ void fwd_hidden(const float* __restrict__ sWT, const float* __restrict__ sb,
-                                           const float2 (&ain)[H], float2 (&aout)[H]) {
+                                           const float2 (&ain)[H], float2 (&aout)[H], const Act<GA> act = Act<GA>{0}) {
   bias2<H>(sb, aout);
   mv_acc<H, H>(sWT, ain, aout);
 #pragma unroll
-  for (int o = 0; o < H; o++) aout[o] = tanh2(aout[o]);
+  for (int o = 0; o < H; o++) aout[o] = act.f(aout[o]);
 }
 
 // y = b4 + w4 . a3
@@ -257,19 +309,18 @@ __device__ __forceinline__ float2 fwd_out(const float* __restrict__ sw4, const f
   return fadd2(y0, y1);
 }
 
-// g = (1 - a^2) * u   (tanh': phi'(z) = 1 - a^2)
-template <int H>
-__device__ __forceinline__ void dtanh_mul(const float2 (&a)[H], const float2 (&u)[H], float2 (&g)[H]) {
+// g = phi'(z) * u   (Tanh: phi'(z) = 1 - a^2)
+template <int H, bool GA = false>
+__device__ __forceinline__ void dtanh_mul(const float2 (&a)[H], const float2 (&u)[H], float2 (&g)[H],
+                                          const Act<GA> act = Act<GA>{0}) {
 #pragma unroll
-  for (int o = 0; o < H; o++) {
-    const float2 d = ffma2(make_float2(-a[o].x, -a[o].y), a[o], splat(1.0f));
-    g[o] = fmul2(d, u[o]);
-  }
+  for (int o = 0; o < H; o++) g[o] = fmul2(act.d1(a[o]), u[o]);
 }
 
-// g3 = (1 - a3^2) * w4
-template <int H>
-__device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const float2 (&a3)[H], float2 (&g3)[H]) {
+// g3 = phi'(z3) * w4
+template <int H, bool GA = false>
+__device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const float2 (&a3)[H], float2 (&g3)[H],
+                                        const Act<GA> act = Act<GA>{0}) {
 #pragma unroll
   for (int q = 0; q < H / 4; q++) {
     const float4 w = *reinterpret_cast<const float4*>(sw4 + 4 * q);
@@ -277,8 +328,7 @@ __device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const flo
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int o = 4 * q + r;
-      const float2 d = ffma2(make_float2(-a3[o].x, -a3[o].y), a3[o], splat(1.0f));
-      g3[o] = fmul2(d, splat(ww[r]));
+      g3[o] = fmul2(act.d1(a3[o]), splat(ww[r]));
     }
   }
 }
@@ -404,12 +454,14 @@ constexpr int P1_THREADS = 256;
 
 // MD: per-row metric - u0 = W1^T g1 of every net goes to U[net][tile][j][256] for k_metric, which also produces the energy
 // sums (this kernel then leaves the E slots of its partial sums at zero)
-template <int H, int K, bool MD = false>
+// GA: general activation (run-time id `act_id`, see Act) instead of Tanh
+template <int H, int K, bool MD = false, bool GA = false>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, int d, int d_pad,
         const float* __restrict__ pw, float* __restrict__ ybuf, double* __restrict__ part,
-        float* __restrict__ U = nullptr) {
+        float* __restrict__ U = nullptr, int act_id = 0) {
   constexpr int NS = 1 + 2 * K + K * (K + 1) / 2;
+  const Act<GA> act{act_id};
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
   const PackLayout<H> L(d_pad);
@@ -434,15 +486,15 @@ k_pass1(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B, i
     for (int net = 0; net < K; net++) {
       const float* s = sw + net * pwn;
       float2 a1[H], a2[H], a3[H], g[H], u[H];
-      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1);
-      fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
-      fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a3);
+      fwd_layer1<H, 8, GA>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1, act);
+      fwd_hidden<H, GA>(s + L.W2T(), s + L.b2(), a1, a2, act);
+      fwd_hidden<H, GA>(s + L.W3T(), s + L.b3(), a2, a3, act);
       const float2 y = fwd_out<H>(s + L.w4(), s + L.b4(), a3);
-      jac_top<H>(s + L.w4(), a3, g);                    // g3
+      jac_top<H, GA>(s + L.w4(), a3, g, act);           // g3
       zero2(u); mv_acc<H, H>(s + L.W3(), g, u);         // u2 = W3^T g3
-      dtanh_mul<H>(a2, u, g);                           // g2
+      dtanh_mul<H, GA>(a2, u, g, act);                  // g2
       zero2(u); mv_acc<H, H>(s + L.W2(), g, u);         // u1 = W2^T g2
-      dtanh_mul<H>(a1, u, g);                           // g1
+      dtanh_mul<H, GA>(a1, u, g, act);                  // g1
       float2 e;
       if (MD) {                                         // u0 = W1^T g1 -> U; e = u0^T M_r u0 is k_metric's
         u0_store<H>(s + L.W1c(), g, d, U + ((size_t)(net * ntiles + n0 / GT) * d) * GT + (n0 % GT), GT);
@@ -617,11 +669,12 @@ __device__ __forceinline__ void row_sum(const float* __restrict__ row, float* __
   *out += (s.x + s.y) + (s.z + s.w);
 }
 
-template <int H, bool MD = false>
+template <int H, bool MD = false, bool GA = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
         int d, int d_pad, int K, const float* __restrict__ pw, const float* __restrict__ ybuf,
-        const Coef* __restrict__ coef, float* __restrict__ pg, const float* __restrict__ U = nullptr) {
+        const Coef* __restrict__ coef, float* __restrict__ pg, const float* __restrict__ U = nullptr, int act_id = 0) {
+  const Act<GA> act{act_id};
   static_assert(H == 20, "outer-product tiling (4x5 tiles, row stride 5) is written for H = 20");
   extern __shared__ float4 smem4[];
   const RowMap<H> R(d);
@@ -687,28 +740,28 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
       const float2 ebar = make_float2(wn.x * ecoef, wn.y * ecoef);
       float2 a[H], g[H], u[H];
       // layer 1: x columns software-pipelined 16 ahead (one warp per scheduler: deeper than k_pass1)
-      fwd_layer1<H, 16>(sw + L.W1c(), sw + L.b1(), xtile + col, d, d_pad, a);
+      fwd_layer1<H, 16, GA>(sw + L.W1c(), sw + L.b1(), xtile + col, d, d_pad, a, act);
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.A1() + o) = a[o];
-      fwd_hidden<H>(sw + L.W2T(), sw + L.b2(), a, g);                  // g := a2
+      fwd_hidden<H, GA>(sw + L.W2T(), sw + L.b2(), a, g, act);         // g := a2
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.A2() + o) = g[o];
-      fwd_hidden<H>(sw + L.W3T(), sw + L.b3(), g, a);                  // a := a3
+      fwd_hidden<H, GA>(sw + L.W3T(), sw + L.b3(), g, a, act);         // a := a3
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.A3() + o) = a[o];
-      jac_top<H>(sw + L.w4(), a, g);                                   // g := g3
+      jac_top<H, GA>(sw + L.w4(), a, g, act);                          // g := g3
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.G3() + o) = g[o];
       zero2(u); mv_acc<H, H>(sw + L.W3(), g, u);                       // u2 = W3^T g3
 #pragma unroll
       for (int o = 0; o < H; o++) a[o] = ROW2(R.A2() + o);             // a := a2
-      dtanh_mul<H>(a, u, g);                                           // g := g2
+      dtanh_mul<H, GA>(a, u, g, act);                                  // g := g2
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.G2() + o) = g[o];
       zero2(u); mv_acc<H, H>(sw + L.W2(), g, u);                       // u1 = W2^T g2
 #pragma unroll
       for (int o = 0; o < H; o++) a[o] = ROW2(R.A1() + o);             // a := a1
-      dtanh_mul<H>(a, u, g);                                           // g := g1
+      dtanh_mul<H, GA>(a, u, g, act);                                  // g := g1
 #pragma unroll
       for (int o = 0; o < H; o++) ROW2(R.G1() + o) = g[o];
       const float2 e2 = make_float2(2.f * ebar.x, 2.f * ebar.y);
@@ -756,31 +809,31 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 #pragma unroll
       for (int o = 0; o < H; o++) {
         const float2 gb = fmul2(e2, u[o]);                             // gbar1
-        const float2 dd = ffma2(make_float2(-a[o].x, -a[o].y), a[o], splat(1.0f));
+        const float2 dd = act.d1(a[o]);
         u[o] = fmul2(dd, gb);                                          // ubar1
         ROW2(R.U1() + o) = u[o];
-        ze1[o] = fmul2(fmul2(make_float2(-2.f * a[o].x, -2.f * a[o].y), g[o]), gb);   // phi'' u1 gbar1
+        ze1[o] = fmul2(fmul2(act.r(a[o]), g[o]), gb);                  // phi'' u1 gbar1
       }
       // ---- layer 2: gbar2 = W2 ubar1
       zero2(g); mv_acc<H, H>(sw + L.W2T(), u, g);                      // g := gbar2
 #pragma unroll
       for (int o = 0; o < H; o++) {
         const float2 a2 = ROW2(R.A2() + o), g2 = ROW2(R.G2() + o);
-        const float2 dd = ffma2(make_float2(-a2.x, -a2.y), a2, splat(1.0f));
+        const float2 dd = act.d1(a2);
         u[o] = fmul2(dd, g[o]);                                        // ubar2
         ROW2(R.U2() + o) = u[o];
-        ze2[o] = fmul2(fmul2(make_float2(-2.f * a2.x, -2.f * a2.y), g2), g[o]);
+        ze2[o] = fmul2(fmul2(act.r(a2), g2), g[o]);
       }
       // ---- layer 3: gbar3 = W3 ubar2
       zero2(g); mv_acc<H, H>(sw + L.W3T(), u, g);                      // g := gbar3
 #pragma unroll
       for (int o = 0; o < H; o++) {
         const float2 a3 = ROW2(R.A3() + o), g3 = ROW2(R.G3() + o);
-        const float2 dd = ffma2(make_float2(-a3.x, -a3.y), a3, splat(1.0f));
+        const float2 dd = act.d1(a3);
         const float2 ub3 = fmul2(dd, g[o]);                            // ubar3 -> d/d w4 (g_4 = 1)
         ROW2(R.S4() + o) = ffma2(ybar, a3, ub3);                       // ubar3 + ybar a3
-        // zbar3 = phi'' u3 gbar3 + phi' w4 ybar = g3 (-2 a3 gbar3 + ybar)
-        const float2 t = ffma2(make_float2(-2.f * a3.x, -2.f * a3.y), g[o], ybar);
+        // zbar3 = phi'' u3 gbar3 + phi' w4 ybar = g3 (r(a3) gbar3 + ybar),  r = phi'' / phi' (Tanh: -2 a3)
+        const float2 t = ffma2(act.r(a3), g[o], ybar);
         ROW2(R.Z3() + o) = fmul2(g3, t);
       }
       ROW2(R.YB()) = ybar;
@@ -830,7 +883,7 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 #pragma unroll
       for (int o = 0; o < H; o++) {
         const float2 a2 = ROW2(R.A2() + o);
-        const float2 dd = ffma2(make_float2(-a2.x, -a2.y), a2, splat(1.0f));
+        const float2 dd = act.d1(a2);
         z[o] = ffma2(dd, t[o], ze2[o]);                                // zbar2
         ROW2(R.Z2() + o) = z[o];
       }
@@ -838,7 +891,7 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 #pragma unroll
       for (int o = 0; o < H; o++) {
         const float2 a1 = ROW2(R.A1() + o);
-        const float2 dd = ffma2(make_float2(-a1.x, -a1.y), a1, splat(1.0f));
+        const float2 dd = act.d1(a1);
         ROW2(R.Z1() + o) = ffma2(dd, t[o], ze1[o]);                    // zbar1
       }
       for (int j = d; j < R.xr; j++) ROW2(R.XT() + j) = make_float2(0.f, 0.f);
@@ -973,10 +1026,11 @@ k_fin2(const float* __restrict__ pg, int ncta, int K, int d, int d_pad,
 }
 
 // forward only: y[B][K]
-template <int H>
+template <int H, bool GA = false>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 k_forward(const float* __restrict__ xt, int64_t B, int d, int d_pad, int K,
-          const float* __restrict__ pw, float* __restrict__ y) {
+          const float* __restrict__ pw, float* __restrict__ y, int act_id = 0) {
+  const Act<GA> act{act_id};
   extern __shared__ float4 smem4[];
   float* sw = reinterpret_cast<float*>(smem4);
   const PackLayout<H> L(d_pad);
@@ -992,9 +1046,9 @@ k_forward(const float* __restrict__ xt, int64_t B, int d, int d_pad, int K,
     for (int net = 0; net < K; net++) {
       const float* s = sw + net * pwn;
       float2 a1[H], a2[H];
-      fwd_layer1<H>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1);
-      fwd_hidden<H>(s + L.W2T(), s + L.b2(), a1, a2);
-      fwd_hidden<H>(s + L.W3T(), s + L.b3(), a2, a1);
+      fwd_layer1<H, 8, GA>(s + L.W1c(), s + L.b1(), xcol, d, d_pad, a1, act);
+      fwd_hidden<H, GA>(s + L.W2T(), s + L.b2(), a1, a2, act);
+      fwd_hidden<H, GA>(s + L.W3T(), s + L.b3(), a2, a1, act);
       const float2 yy = fwd_out<H>(s + L.w4(), s + L.b4(), a1);
       y[n0 * K + net] = yy.x;
       if (v1) y[n1 * K + net] = yy.y;

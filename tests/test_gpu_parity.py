@@ -623,3 +623,36 @@ def test_gather_look_ahead_equals_plain_steps(d, k, B):
     c["idx"] = idxs[5].cpu().numpy()
     res = ahead.step(c["idx"], flat, c["alpha"])             # host-facing call after a look-ahead chain
     _check(c, _oracle(c), res)
+
+
+@pytest.mark.parametrize("act", ["Softplus", "LogSigmoid", "ELU", "CELU", "ReLU"])
+def test_fused_kernels_with_other_activations_vs_oracle(act):
+    """phi, phi', phi'' as a parameter of the fused kernels.  The reference takes any torch.nn activation
+    (src/network_arch.py:27-34); for the 20-20-20 architecture the FFMA2 kernels run every activation whose derivatives are
+    functions of its value (Act<true> in csrc/epde_fused.cuh), against the oracle and against the layer-wise family."""
+    from eigenpde_nn_b200.engine import StepEngine
+    c = _rand_case(50 + len(act), 12, 3, [20, 20, 20], 3000, 1531, act=act, scale=0.5)
+    ref = _oracle(c)
+    tol = TOL
+    outs = []
+    for generic in (False, True):
+        eng = StepEngine(c["X"], c["w"], c["arch"], c["k"], c["act"], c["diag_coeff"], c["beta"], c["eig_w"], generic=generic)
+        assert eng.fused == (not generic)
+        res = eng.step(c["idx"], _flat(c["params"]), c["alpha"])
+        grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), c["arch"], c["k"])
+        check_step_against(ref, res, tol, grads)
+        outs.append(res)
+        y = eng.forward(torch.from_numpy(c["idx"]).cuda(), len(c["idx"]), _flat(c["params"])).cpu().numpy()
+        want = closed_form.forward_only(c["params"], c["X"][c["idx"]], c["act"] if c["act"] in closed_form.ACTIVATIONS else "CELU")
+        assert np.abs(y - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("act", ["Tanhshrink", "Sigmoid"])
+def test_activations_that_stay_on_the_layer_wise_family(act):
+    c = _rand_case(91, 12, 2, [20, 20, 20], 2000, 700, act=act, scale=0.5)
+    eng = _engine(c)
+    assert not eng.fused
+    res = eng.step(c["idx"], _flat(c["params"]), c["alpha"])
+    grads = unflatten(res["grad"].cpu().numpy().astype(np.float64), c["arch"], c["k"])
+    # all-positive Sigmoid units: ill-conditioned in fp32 like the golden act_sigmoid_6d_k3 case (ILL_CONDITIONED)
+    check_step_against(_oracle(c), res, 2e-4 if act == "Sigmoid" else TOL, grads)
