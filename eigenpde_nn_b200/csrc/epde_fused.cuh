@@ -243,6 +243,53 @@ struct Act {
     if (!GA) return make_float2(-2.f * a.x, -2.f * a.y);
     return make_float2(rs(a.x), rs(a.y));
   }
+  // Whole-vector forms: the (CTA-uniform) switch sits OUTSIDE the unrolled loop over the H units, so that the H independent
+  // evaluations of a case overlap (with the switch per element they ran one after the other: 5x slower kernels).
+#define EPDE_ACT_CASES(EXPR_SIG, EXPR_SP, EXPR_LS, EXPR_ELU, EXPR_RELU)                         \
+    switch (id) {                                                                               \
+      case EPDE_ACT_SIGMOID:    { _Pragma("unroll") for (int o = 0; o < H; o++) { EXPR_SIG; } break; }   \
+      case EPDE_ACT_SOFTPLUS:   { _Pragma("unroll") for (int o = 0; o < H; o++) { EXPR_SP; } break; }    \
+      case EPDE_ACT_LOGSIGMOID: { _Pragma("unroll") for (int o = 0; o < H; o++) { EXPR_LS; } break; }    \
+      case EPDE_ACT_ELU:        { _Pragma("unroll") for (int o = 0; o < H; o++) { EXPR_ELU; } break; }   \
+      default:                  { _Pragma("unroll") for (int o = 0; o < H; o++) { EXPR_RELU; } break; }  \
+    }
+  template <int H>
+  __device__ __forceinline__ void f_all(float2 (&a)[H]) const {                 // a <- phi(a)
+    if (!GA) {
+#pragma unroll
+      for (int o = 0; o < H; o++) a[o] = tanh2(a[o]);
+      return;
+    }
+#define EPDE_F2(ID) a[o] = make_float2(Act<true>{ID}.f1(a[o].x), Act<true>{ID}.f1(a[o].y))
+    EPDE_ACT_CASES(EPDE_F2(EPDE_ACT_SIGMOID), EPDE_F2(EPDE_ACT_SOFTPLUS), EPDE_F2(EPDE_ACT_LOGSIGMOID), EPDE_F2(EPDE_ACT_ELU),
+                   EPDE_F2(EPDE_ACT_RELU))
+#undef EPDE_F2
+  }
+  template <int H>
+  __device__ __forceinline__ void d1_all(const float2 (&a)[H], float2 (&dd)[H]) const {      // dd = phi'(z)
+    if (!GA) {
+#pragma unroll
+      for (int o = 0; o < H; o++) dd[o] = ffma2(make_float2(-a[o].x, -a[o].y), a[o], splat(1.0f));
+      return;
+    }
+#define EPDE_D2(ID) dd[o] = make_float2(Act<true>{ID}.d1s(a[o].x), Act<true>{ID}.d1s(a[o].y))
+    EPDE_ACT_CASES(EPDE_D2(EPDE_ACT_SIGMOID), EPDE_D2(EPDE_ACT_SOFTPLUS), EPDE_D2(EPDE_ACT_LOGSIGMOID), EPDE_D2(EPDE_ACT_ELU),
+                   EPDE_D2(EPDE_ACT_RELU))
+#undef EPDE_D2
+  }
+  template <int H>
+  __device__ __forceinline__ void r_all(const float2 (&a)[H], float2 (&rr)[H]) const {       // rr = phi''(z) / phi'(z)
+    if (!GA) {
+#pragma unroll
+      for (int o = 0; o < H; o++) rr[o] = make_float2(-2.f * a[o].x, -2.f * a[o].y);
+      return;
+    }
+#define EPDE_R2(ID) rr[o] = make_float2(Act<true>{ID}.rs(a[o].x), Act<true>{ID}.rs(a[o].y))
+    EPDE_ACT_CASES(EPDE_R2(EPDE_ACT_SIGMOID), EPDE_R2(EPDE_ACT_SOFTPLUS), EPDE_R2(EPDE_ACT_LOGSIGMOID), EPDE_R2(EPDE_ACT_ELU),
+                   EPDE_R2(EPDE_ACT_RELU))
+#undef EPDE_R2
+  }
+#undef EPDE_ACT_CASES
 };
 
 // layer 1: a1 = tanh(W1 x + b1); x_j of the sample pair is one coalesced float2 of the transposed
@@ -279,8 +326,7 @@ __device__ __forceinline__ void fwd_layer1(const float* __restrict__ sW1T, const
 #pragma unroll
     for (int q = 0; q < PF; q++) cur[q] = nxt[q];
   }
-#pragma unroll
-  for (int o = 0; o < H; o++) a1[o] = act.f(a1[o]);
+  act.f_all(a1);
 }
 
 // hidden layer: a_out = tanh(W a_in + b), weights in [in][out] layout
@@ -289,8 +335,7 @@ __device__ __forceinline__ void fwd_hidden(const float* __restrict__ sWT, const 
                                            const float2 (&ain)[H], float2 (&aout)[H], const Act<GA> act = Act<GA>{0}) {
   bias2<H>(sb, aout);
   mv_acc<H, H>(sWT, ain, aout);
-#pragma unroll
-  for (int o = 0; o < H; o++) aout[o] = act.f(aout[o]);
+  act.f_all(aout);
 }
 
 // y = b4 + w4 . a3
@@ -313,14 +358,18 @@ __device__ __forceinline__ float2 fwd_out(const float* __restrict__ sw4, const f
 template <int H, bool GA = false>
 __device__ __forceinline__ void dtanh_mul(const float2 (&a)[H], const float2 (&u)[H], float2 (&g)[H],
                                           const Act<GA> act = Act<GA>{0}) {
+  float2 dd[H];
+  act.d1_all(a, dd);
 #pragma unroll
-  for (int o = 0; o < H; o++) g[o] = fmul2(act.d1(a[o]), u[o]);
+  for (int o = 0; o < H; o++) g[o] = fmul2(dd[o], u[o]);
 }
 
 // g3 = phi'(z3) * w4
 template <int H, bool GA = false>
 __device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const float2 (&a3)[H], float2 (&g3)[H],
                                         const Act<GA> act = Act<GA>{0}) {
+  float2 dd[H];
+  act.d1_all(a3, dd);
 #pragma unroll
   for (int q = 0; q < H / 4; q++) {
     const float4 w = *reinterpret_cast<const float4*>(sw4 + 4 * q);
@@ -328,7 +377,7 @@ __device__ __forceinline__ void jac_top(const float* __restrict__ sw4, const flo
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int o = 4 * q + r;
-      g3[o] = fmul2(act.d1(a3[o]), splat(ww[r]));
+      g3[o] = fmul2(dd[o], splat(ww[r]));
     }
   }
 }
@@ -806,35 +855,48 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
       } else {
         zero2(u); mv_acc<H, H>(sw + L.Km(), g, u);                     // t = K g1
       }
+      {
+        float2 dv[H], rv[H];
+        act.d1_all(a, dv); act.r_all(a, rv);
 #pragma unroll
-      for (int o = 0; o < H; o++) {
-        const float2 gb = fmul2(e2, u[o]);                             // gbar1
-        const float2 dd = act.d1(a[o]);
-        u[o] = fmul2(dd, gb);                                          // ubar1
-        ROW2(R.U1() + o) = u[o];
-        ze1[o] = fmul2(fmul2(act.r(a[o]), g[o]), gb);                  // phi'' u1 gbar1
+        for (int o = 0; o < H; o++) {
+          const float2 gb = fmul2(e2, u[o]);                           // gbar1
+          u[o] = fmul2(dv[o], gb);                                     // ubar1
+          ROW2(R.U1() + o) = u[o];
+          ze1[o] = fmul2(fmul2(rv[o], g[o]), gb);                      // phi'' u1 gbar1
+        }
       }
       // ---- layer 2: gbar2 = W2 ubar1
       zero2(g); mv_acc<H, H>(sw + L.W2T(), u, g);                      // g := gbar2
+      {
+        float2 av[H], dv[H], rv[H];
 #pragma unroll
-      for (int o = 0; o < H; o++) {
-        const float2 a2 = ROW2(R.A2() + o), g2 = ROW2(R.G2() + o);
-        const float2 dd = act.d1(a2);
-        u[o] = fmul2(dd, g[o]);                                        // ubar2
-        ROW2(R.U2() + o) = u[o];
-        ze2[o] = fmul2(fmul2(act.r(a2), g2), g[o]);
+        for (int o = 0; o < H; o++) av[o] = ROW2(R.A2() + o);
+        act.d1_all(av, dv); act.r_all(av, rv);
+#pragma unroll
+        for (int o = 0; o < H; o++) {
+          const float2 g2 = ROW2(R.G2() + o);
+          u[o] = fmul2(dv[o], g[o]);                                   // ubar2
+          ROW2(R.U2() + o) = u[o];
+          ze2[o] = fmul2(fmul2(rv[o], g2), g[o]);
+        }
       }
       // ---- layer 3: gbar3 = W3 ubar2
       zero2(g); mv_acc<H, H>(sw + L.W3T(), u, g);                      // g := gbar3
+      {
+        float2 av[H], dv[H], rv[H];
 #pragma unroll
-      for (int o = 0; o < H; o++) {
-        const float2 a3 = ROW2(R.A3() + o), g3 = ROW2(R.G3() + o);
-        const float2 dd = act.d1(a3);
-        const float2 ub3 = fmul2(dd, g[o]);                            // ubar3 -> d/d w4 (g_4 = 1)
-        ROW2(R.S4() + o) = ffma2(ybar, a3, ub3);                       // ubar3 + ybar a3
-        // zbar3 = phi'' u3 gbar3 + phi' w4 ybar = g3 (r(a3) gbar3 + ybar),  r = phi'' / phi' (Tanh: -2 a3)
-        const float2 t = ffma2(act.r(a3), g[o], ybar);
-        ROW2(R.Z3() + o) = fmul2(g3, t);
+        for (int o = 0; o < H; o++) av[o] = ROW2(R.A3() + o);
+        act.d1_all(av, dv); act.r_all(av, rv);
+#pragma unroll
+        for (int o = 0; o < H; o++) {
+          const float2 g3 = ROW2(R.G3() + o);
+          const float2 ub3 = fmul2(dv[o], g[o]);                       // ubar3 -> d/d w4 (g_4 = 1)
+          ROW2(R.S4() + o) = ffma2(ybar, av[o], ub3);                  // ubar3 + ybar a3
+          // zbar3 = phi'' u3 gbar3 + phi' w4 ybar = g3 (r(a3) gbar3 + ybar),  r = phi'' / phi' (Tanh: -2 a3)
+          const float2 t = ffma2(rv[o], g[o], ybar);
+          ROW2(R.Z3() + o) = fmul2(g3, t);
+        }
       }
       ROW2(R.YB()) = ybar;
     }
@@ -880,19 +942,25 @@ k_pass2(const float* __restrict__ xt, const float* __restrict__ wt, int64_t B,
 #pragma unroll
       for (int o = 0; o < H; o++) z[o] = ROW2(R.Z3() + o);
       zero2(t); mv_acc<H, H>(sw + L.W3(), z, t);                       // W3^T zbar3
+      {
+        float2 av[H], dv[H];
 #pragma unroll
-      for (int o = 0; o < H; o++) {
-        const float2 a2 = ROW2(R.A2() + o);
-        const float2 dd = act.d1(a2);
-        z[o] = ffma2(dd, t[o], ze2[o]);                                // zbar2
-        ROW2(R.Z2() + o) = z[o];
+        for (int o = 0; o < H; o++) av[o] = ROW2(R.A2() + o);
+        act.d1_all(av, dv);
+#pragma unroll
+        for (int o = 0; o < H; o++) {
+          z[o] = ffma2(dv[o], t[o], ze2[o]);                           // zbar2
+          ROW2(R.Z2() + o) = z[o];
+        }
       }
       zero2(t); mv_acc<H, H>(sw + L.W2(), z, t);                       // W2^T zbar2
+      {
+        float2 av[H], dv[H];
 #pragma unroll
-      for (int o = 0; o < H; o++) {
-        const float2 a1 = ROW2(R.A1() + o);
-        const float2 dd = act.d1(a1);
-        ROW2(R.Z1() + o) = ffma2(dd, t[o], ze1[o]);                    // zbar1
+        for (int o = 0; o < H; o++) av[o] = ROW2(R.A1() + o);
+        act.d1_all(av, dv);
+#pragma unroll
+        for (int o = 0; o < H; o++) ROW2(R.Z1() + o) = ffma2(dv[o], t[o], ze1[o]);      // zbar1
       }
       for (int j = d; j < R.xr; j++) ROW2(R.XT() + j) = make_float2(0.f, 0.f);
       asm volatile("cp.async.wait_group 0;" ::: "memory");

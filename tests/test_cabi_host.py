@@ -43,7 +43,10 @@ def test_param_count_and_sums(L):
     D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Tanh", 52)
     assert L.epde_has_fused_path(C.byref(D)) == 1
     D = _lib.make_desc([50, 20, 20, 20, 1], 3, "Softplus", 52)
-    assert L.epde_has_fused_path(C.byref(D)) == 0
+    assert L.epde_has_fused_path(C.byref(D)) == 1          # FFMA2 kernels with the activation as a parameter
+    for name in ("Tanhshrink", "Sigmoid"):                  # stay on the layer-wise family
+        D = _lib.make_desc([50, 20, 20, 20, 1], 3, name, 52)
+        assert L.epde_has_fused_path(C.byref(D)) == 0
     D = _lib.make_desc([50, 256, 256, 256, 256, 1], 4, "Tanh", 52)
     assert L.epde_has_fused_path(C.byref(D)) == 0
 
