@@ -112,8 +112,11 @@ int epde_param_count(const epde_desc* desc, int64_t* out);
  * src/pytorch_eigen_solver.py:169-173,215 and :186 */
 int epde_num_sums(const epde_desc* desc, int32_t* out);
 
-/* 1 if the fused FFMA2 kernel family covers this descriptor, 0 if the generic layer-wise
- * kernels are used; negative on a malformed descriptor */
+/* 1 if fused kernels cover this descriptor, 0 if the generic layer-wise kernels are used; negative on a malformed
+ * descriptor.  Fused: d -> 20 -> 20 -> 20 -> 1 with d <= 60 and k <= 6; Tanh on the tcgen05 kernels (or the FFMA2 kernels with
+ * EPDE_FLAG_FFMA2 / a per-row metric with d <= 40), Softplus / LogSigmoid / ELU (= CELU) / ReLU on the FFMA2 kernels
+ * (src/network_arch.py:27-34 takes any torch.nn activation); everything else - other widths or depths, Sigmoid, Tanhshrink,
+ * EPDE_FLAG_GENERIC - runs layer-wise. */
 int epde_has_fused_path(const epde_desc* desc);
 
 int epde_workspace_bytes(const epde_desc* desc, int64_t B, size_t* out);
